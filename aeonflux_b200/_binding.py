@@ -1,0 +1,67 @@
+"""ctypes binding of the C ABI in include/aeonflux_b200.h (the stub a reference maintainer's FFI would mirror,
+see INTEGRATION.md).  `Binding` wraps an already-loaded library handle; `aeonflux_b200._lib.load()` is the only place the
+package loads one, and it loads the CUDA build or fails."""
+import ctypes
+
+import numpy as np
+
+AFX_OK = 0
+
+
+class afx_presentation_batch(ctypes.Structure):
+    _fields_ = [("n_attrs", ctypes.c_uint16), ("kinds", ctypes.c_char_p), ("count", ctypes.c_size_t),
+                ("fields", ctypes.POINTER(ctypes.c_void_p)), ("n_fields", ctypes.c_size_t)]
+
+
+class afx_debug_dump(ctypes.Structure):
+    _fields_ = [("Z", ctypes.c_void_p), ("commitments", ctypes.c_void_p), ("challenges", ctypes.c_void_p), ("status", ctypes.c_void_p)]
+
+
+class AfxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("aeonflux_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Binding:
+    SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
+               "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
+               "afx_launch_count", "afx_ctx_device", "afx_strerror", "afx_version"]
+
+    def __init__(self, cdll):
+        L = self.L = cdll
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        L.afx_ctx_create.restype = ctypes.c_int
+        L.afx_ctx_create.argtypes = [vp, sz, vp, vp, sz, ctypes.c_int, sz, ctypes.POINTER(vp)]
+        L.afx_ctx_destroy.restype = None
+        L.afx_ctx_destroy.argtypes = [vp]
+        for f in ("afx_presentation_num_fields", "afx_presentation_num_commitments", "afx_presentation_num_proofs"):
+            getattr(L, f).restype = sz
+            getattr(L, f).argtypes = [ctypes.c_uint16, ctypes.c_char_p]
+        L.afx_verify_presentations.restype = ctypes.c_int
+        L.afx_verify_presentations.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(afx_debug_dump)]
+        L.afx_verify_issuances.restype = ctypes.c_int
+        L.afx_verify_issuances.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(afx_debug_dump)]
+        L.afx_verify_presentations_device.restype = ctypes.c_int
+        L.afx_verify_presentations_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp]
+        L.afx_launch_count.restype = ctypes.c_uint64
+        L.afx_launch_count.argtypes = [vp]
+        L.afx_ctx_device.restype = ctypes.c_int
+        L.afx_ctx_device.argtypes = [vp]
+        L.afx_strerror.restype = ctypes.c_char_p
+        L.afx_strerror.argtypes = [ctypes.c_int]
+        L.afx_version.restype = ctypes.c_char_p
+
+    def check(self, rc):
+        if rc != AFX_OK:
+            raise AfxError(rc, self.L.afx_strerror(rc).decode())
+
+    def version(self):
+        return self.L.afx_version().decode()
+
+
+def _as_fields(fields):
+    """fields: ndarray [n_fields][count][32] uint8 (or a list of [count][32] arrays) -> (ctypes pointer array, keepalive)"""
+    arrs = [np.ascontiguousarray(f, dtype=np.uint8) for f in fields]
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return ptrs, arrs

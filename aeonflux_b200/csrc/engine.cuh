@@ -1,0 +1,350 @@
+// The batch engine's stage bodies, shared by the CUDA kernels (afx_b200.cu) and the test-only host emulation
+// harness (tests/hostemu).  One "item" = one presentation / issuance of a batch; every stage is data-parallel over
+// items with no cross-item state.
+//
+// Stages for Issuer::verify (/root/reference/src/issuer.rs:141-147 -> nizk/presentation.rs:324-443):
+//   points     decompress every input point once, derive sums/differences, build the [1P..8P] Niels table each
+//              ladder needs, compress the derived points the transcript absorbs (presentation.rs:373-412 do this with
+//              compress()+decompress() per allocated point; SURVEY 8d "minimal schedule")
+//   amac       Z = C_V - W - x0*C_x0 - x1*C_x1 - sum y_i*X_i as ONE constant-schedule radix-16 Straus ladder over
+//              issuer-secret scalars (presentation.rs:342-352: seven separate constant-time scalar mults)
+//   msm        one thread per (item, constraint): R = sum resp_k*P_k - c*LHS, fixed-window ladder sharing 252 doublings,
+//              radix-256 affine tables for per-issuer constant bases, radix-16 tables for per-item bases; compress R
+//              (zkp verify_compact's vartime_multiscalar_mul per constraint)
+//   transcript one thread per (item, proof): Merlin/STROBE/Keccak-f[1600] over the compiled block template, 64-byte
+//              challenge squeeze, reduction mod l, compare with the claimed challenge
+//   verdict    status word -> 0 (Ok) / 1 (VerificationFailure)
+#pragma once
+#include "fe.cuh"
+#include "ge.cuh"
+#include "keccak.cuh"
+#include "sc.cuh"
+
+namespace afx {
+
+constexpr int MAX_ATTRS = 32;
+constexpr int MAX_VAR_TERMS = MAX_ATTRS + 4;
+constexpr int MAX_CONST_TERMS = MAX_ATTRS + 8;
+constexpr int CTAB_ENTRIES = 128;  // radix-256 signed digits: multiples 1..128 of a constant base
+
+// ---- scalar sources ---------------------------------------------------------------------------
+enum : u32 { SC_FIELD = 0, SC_MUL = 1, SC_MULADD = 2 };  // F[f0] | F[f0]*F[f1] | F[f0] + F[f1]*F[f2]
+struct ScalarSrc { u16 op, f0, f1, f2; };
+
+struct VarTerm { u16 table_slot; u16 neg; ScalarSrc s; };
+struct ConstTerm { u16 ctab; u16 neg; ScalarSrc s; };
+struct MsmDesc {
+    u16 nvar, ncon, out_slot, pad;
+    VarTerm var[MAX_VAR_TERMS];
+    ConstTerm con[MAX_CONST_TERMS];
+};
+
+enum : u32 { PJ_COPY = 0, PJ_ADD = 1, PJ_SUB = 2 };
+struct PointJob {
+    int16_t field_a, field_b;      // input point fields (field_b = -1 for PJ_COPY)
+    u16 op, pad;
+    int16_t table_slot, ext_slot;  // -1 = not written
+    int16_t comp_slot, compneg_slot;  // compressed encoding of the point / of its negation
+};
+
+struct AmacVar { u16 table_slot, digit_row; };
+struct AmacPs { u16 ctab, y_row, field_m, pad; };  // (y_i * m_i) * G_m[i] for a revealed scalar attribute
+struct AmacDesc {
+    u16 ext_cv, nvar, nps, out_table_slot, out_comp_slot, pad;
+    AmacVar var[MAX_ATTRS + 2];
+    AmacPs ps[MAX_ATTRS];
+};
+
+enum : u32 { SRC_FIELD = 0, SRC_COMP = 1, SRC_COMMIT = 2 };
+struct TxHole { u16 block, off, len, src_off; u16 src_kind, src_idx; };
+struct TxIdCheck { u16 src_kind, src_idx; };
+struct TxDesc {
+    u32 nblocks, block_ofs;   // blocks: 21 u64 lanes each, at lanes[block_ofs*21]
+    u32 nholes, hole_ofs;
+    u32 nid, id_ofs;
+    u16 chal_field, out_slot;
+    u64 midstate[25];
+};
+
+// ---- workspace ------------------------------------------------------------------------------------
+// All arrays are slot-major then item-major; an item's 32-byte word is 8 consecutive u32 (two 128-bit loads).
+struct Workspace {
+    u32 count;
+    const u32* fields;   // [n_fields][count][8]
+    u32* tables;         // [n_tables][count][8 entries][32]
+    u32* ext;            // [n_ext][count][32]
+    u32* comp;           // [n_comp][count][8]
+    u32* commit;         // [n_msm][count][8]
+    u32* chal;           // [n_proofs][count][8]  recomputed challenges
+    u32* status;         // [count]   0 = ok so far
+    // per-issuer constants
+    const u32* ctabs;    // [n_ctab][128][24]  affine Niels multiples 1..128
+    const u32* secdig;   // [n_secret][8]      radix-16 recoded secret scalars (packed nibbles)
+    const u32* secsc;    // [n_secret][8]      the same scalars, canonical words
+    const u32* W_pniels; // [32]               W in projective Niels form
+    const u64* lanes;    // transcript block masks
+    const TxHole* holes;
+    const TxIdCheck* idchecks;
+};
+
+enum : u32 { ST_BAD_POINT = 1, ST_BAD_SCALAR = 2, ST_IDENTITY = 4, ST_CHALLENGE = 8 };
+
+// ---- small helpers ----------------------------------------------------------------------------------
+AFX_HD void load8(u32* dst, const u32* src) {
+#if defined(__CUDA_ARCH__)
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+    uint4 a = p[0], b = p[1];
+    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) dst[i] = src[i];
+#endif
+}
+AFX_HD void store8(u32* dst, const u32* src) {
+#if defined(__CUDA_ARCH__)
+    uint4* p = reinterpret_cast<uint4*>(dst);
+    p[0] = make_uint4(src[0], src[1], src[2], src[3]); p[1] = make_uint4(src[4], src[5], src[6], src[7]);
+#else
+    for (int i = 0; i < 8; i++) dst[i] = src[i];
+#endif
+}
+AFX_HD fe load_fe(const u32* src) { fe r; load8(r.v, src); return r; }
+AFX_HD void store_fe(u32* dst, const fe& a) { store8(dst, a.v); }
+AFX_HD ge load_ge(const u32* src) { ge p; p.X = load_fe(src); p.Y = load_fe(src + 8); p.Z = load_fe(src + 16); p.T = load_fe(src + 24); return p; }
+AFX_HD void store_ge(u32* dst, const ge& p) { store_fe(dst, p.X); store_fe(dst + 8, p.Y); store_fe(dst + 16, p.Z); store_fe(dst + 24, p.T); }
+AFX_HD pniels load_pniels(const u32* src) { pniels n; n.YpX = load_fe(src); n.YmX = load_fe(src + 8); n.Z = load_fe(src + 16); n.T2d = load_fe(src + 24); return n; }
+AFX_HD void store_pniels(u32* dst, const pniels& n) { store_fe(dst, n.YpX); store_fe(dst + 8, n.YmX); store_fe(dst + 16, n.Z); store_fe(dst + 24, n.T2d); }
+AFX_HD aniels load_aniels(const u32* src) { aniels n; n.ypx = load_fe(src); n.ymx = load_fe(src + 8); n.xy2d = load_fe(src + 16); return n; }
+
+struct TableStore { u32* dst; AFX_HD void operator()(int e, const pniels& n) const { store_pniels(dst + 32 * e, n); } };
+AFX_HD void store_table8(u32* dst, const ge& p) { TableStore ts{dst}; ge_table8(p, ts); }
+
+AFX_HD const u32* field_ptr(const Workspace& ws, u32 f, u32 item) { return ws.fields + ((size_t)f * ws.count + item) * 8; }
+AFX_HD u32* table_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.tables + ((size_t)slot * ws.count + item) * 256; }
+AFX_HD u32* ext_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.ext + ((size_t)slot * ws.count + item) * 32; }
+AFX_HD u32* comp_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.comp + ((size_t)slot * ws.count + item) * 8; }
+AFX_HD u32* commit_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.commit + ((size_t)slot * ws.count + item) * 8; }
+
+AFX_HD void status_or(const Workspace& ws, u32 item, u32 bits) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(ws.status + item, bits);
+#else
+    ws.status[item] |= bits;
+#endif
+}
+
+AFX_HD sc eval_scalar(const Workspace& ws, const ScalarSrc& s, u32 item) {
+    sc a = sc_from_words(field_ptr(ws, s.f0, item));
+    if (s.op == SC_FIELD) return a;
+    sc b = sc_from_words(field_ptr(ws, s.f1, item));
+    if (s.op == SC_MUL) return sc_mul(a, b);
+    sc c = sc_from_words(field_ptr(ws, s.f2, item));
+    return sc_muladd(b, c, a);
+}
+
+// ---- stage: scalar canonicity ------------------------------------------------------------------------
+AFX_HD void scalar_check_job(const Workspace& ws, u32 field, u32 item) {
+    u32 w[8]; load8(w, field_ptr(ws, field, item));
+    if (!sc_is_canonical(sc_from_words(w))) status_or(ws, item, ST_BAD_SCALAR);
+}
+
+// ---- stage: points --------------------------------------------------------------------------------------
+AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
+    u32 w[8];
+    ge p;
+    load8(w, field_ptr(ws, (u32)j.field_a, item));
+    u32 ok = ge_decompress(p, w);
+    if (j.op != PJ_COPY) {
+        ge q;
+        load8(w, field_ptr(ws, (u32)j.field_b, item));
+        ok &= ge_decompress(q, w);
+        p = (j.op == PJ_ADD) ? ge_add(p, q) : ge_sub(p, q);
+    }
+    if (!ok) status_or(ws, item, ST_BAD_POINT);
+    if (j.ext_slot >= 0) store_ge(ext_ptr(ws, (u32)j.ext_slot, item), p);
+    if (j.comp_slot >= 0) { ge_compress(w, p); store8(comp_ptr(ws, (u32)j.comp_slot, item), w); }
+    if (j.compneg_slot >= 0) { ge_compress(w, ge_neg(p)); store8(comp_ptr(ws, (u32)j.compneg_slot, item), w); }
+    if (j.table_slot >= 0) {
+        store_table8(table_ptr(ws, (u32)j.table_slot, item), p);
+    }
+}
+
+// Constant-address table reads: every entry is loaded and the wanted one kept with masks, so neither the branch
+// pattern nor the address stream depends on the (secret) digit.
+AFX_HD pniels pniels_scan_select(const u32* table, int digit) {
+    u32 neg = (u32)digit >> 31;
+    u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
+    pniels r = pniels_identity();
+    for (u32 e = 1; e <= 8; e++) {
+        pniels c = load_pniels(table + 32 * (e - 1));
+        u32 take = (e == mag);
+        r.YpX = fe_select(r.YpX, c.YpX, take); r.YmX = fe_select(r.YmX, c.YmX, take);
+        r.Z = fe_select(r.Z, c.Z, take); r.T2d = fe_select(r.T2d, c.T2d, take);
+    }
+    return pniels_cneg(r, neg);
+}
+AFX_HD aniels aniels_scan_select8(const u32* ctab, int digit) {
+    u32 neg = (u32)digit >> 31;
+    u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
+    aniels r = aniels_identity();
+    for (u32 e = 1; e <= 8; e++) {
+        aniels c = load_aniels(ctab + 24 * (e - 1));
+        u32 take = (e == mag);
+        r.ypx = fe_select(r.ypx, c.ypx, take); r.ymx = fe_select(r.ymx, c.ymx, take); r.xy2d = fe_select(r.xy2d, c.xy2d, take);
+    }
+    return aniels_cneg(r, neg);
+}
+
+// ---- stage: aMAC --------------------------------------------------------------------------------------------
+// scratch: nps * 8 words per item for the recoded (y_i * m_i) scalars; scratch_stride = distance between words
+AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scratch, u32 scratch_stride) {
+    for (u32 k = 0; k < d.nps; k++) {
+        sc m = sc_from_words(field_ptr(ws, d.ps[k].field_m, item));
+        sc y = sc_from_words(ws.secsc + 8 * d.ps[k].y_row);
+        u32 rec[8];
+        sc_recode16(rec, sc_mul(y, m));
+        for (int w = 0; w < 8; w++) scratch[(k * 8 + w) * scratch_stride] = rec[w];
+    }
+    ge acc = ge_identity();
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+        for (u32 k = 0; k < d.nvar; k++) {
+            int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
+            pniels e = pniels_scan_select(table_ptr(ws, d.var[k].table_slot, item), dig);
+            acc = ge_add_pn(acc, e, true);
+        }
+        for (u32 k = 0; k < d.nps; k++) {
+            u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
+            int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
+            aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.ps[k].ctab * CTAB_ENTRIES * 24, dig);
+            acc = ge_madd(acc, e, true);
+        }
+    }
+    // Z = (C_V - W) - acc
+    ge cv = load_ge(ext_ptr(ws, d.ext_cv, item));
+    ge z = ge_add_pn(cv, pniels_cneg(load_pniels(ws.W_pniels), 1));
+    z = ge_sub(z, acc);
+    u32 w[8];
+    ge_compress(w, z);
+    store8(comp_ptr(ws, d.out_comp_slot, item), w);
+    store_table8(table_ptr(ws, d.out_table_slot, item), z);
+}
+
+// Where constant term k's radix-256 table lives: the first `nstage` are staged in shared memory by the CTA.
+struct CtabResolver {
+    const u32* staged; const u32* global; const MsmDesc* d; u32 nstage;
+    AFX_HD const u32* operator()(u32 k) const {
+        return k < nstage ? staged + (size_t)k * CTAB_ENTRIES * 24 : global + (size_t)d->con[k].ctab * CTAB_ENTRIES * 24;
+    }
+};
+
+// ---- stage: msm -----------------------------------------------------------------------------------------------
+// scratch: (nvar + ncon) * 8 words per item of recoded scalars.  ctab_of(k) returns the table base of constant term k
+// (shared-memory staged on the device, global otherwise).
+template <typename CtabOf>
+AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, CtabOf ctab_of) {
+    for (u32 k = 0; k < d.nvar; k++) {
+        u32 rec[8];
+        sc_recode16(rec, eval_scalar(ws, d.var[k].s, item));
+        for (int w = 0; w < 8; w++) scratch[(k * 8 + w) * scratch_stride] = rec[w];
+    }
+    for (u32 k = 0; k < d.ncon; k++) {
+        u32 rec[8];
+        sc_recode256(rec, eval_scalar(ws, d.con[k].s, item));
+        for (int w = 0; w < 8; w++) scratch[((d.nvar + k) * 8 + w) * scratch_stride] = rec[w];
+    }
+    ge acc = ge_identity();
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+        for (u32 k = 0; k < d.nvar; k++) {
+            u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
+            int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
+            if (dig != 0) {
+                u32 neg = ((u32)dig >> 31) ^ d.var[k].neg;
+                u32 mag = (u32)(dig < 0 ? -dig : dig);
+                pniels e = load_pniels(table_ptr(ws, d.var[k].table_slot, item) + 32 * (mag - 1));
+                acc = ge_add_pn(acc, pniels_cneg(e, neg), true);
+            }
+        }
+        if ((i & 1) == 0) {
+            for (u32 k = 0; k < d.ncon; k++) {
+                u32 word = scratch[((d.nvar + k) * 8 + (i >> 3)) * scratch_stride];
+                int dig = ((int)(word << (24 - 8 * ((i >> 1) & 3)))) >> 24;
+                if (dig != 0) {
+                    u32 neg = ((u32)dig >> 31) ^ d.con[k].neg;
+                    u32 mag = (u32)(dig < 0 ? -dig : dig);
+                    aniels e = load_aniels(ctab_of(k) + 24 * (mag - 1));
+                    acc = ge_madd(acc, aniels_cneg(e, neg), true);
+                }
+            }
+        }
+    }
+    u32 w[8];
+    ge_compress(w, acc);
+    store8(commit_ptr(ws, d.out_slot, item), w);
+}
+
+// ---- stage: transcript -------------------------------------------------------------------------------------------
+AFX_HD const u32* tx_src(const Workspace& ws, u32 kind, u32 idx, u32 item) {
+    if (kind == SRC_FIELD) return field_ptr(ws, idx, item);
+    if (kind == SRC_COMP) return comp_ptr(ws, idx, item);
+    return commit_ptr(ws, idx, item);
+}
+AFX_HD void transcript_job(const Workspace& ws, const TxDesc& d, u32 item) {
+    u64 st[25];
+    for (int i = 0; i < 25; i++) st[i] = d.midstate[i];
+    for (u32 k = 0; k < d.nid; k++) {
+        const TxIdCheck& c = ws.idchecks[d.id_ofs + k];
+        u32 w[8]; load8(w, tx_src(ws, c.src_kind, c.src_idx, item));
+        u32 x = 0;
+        for (int i = 0; i < 8; i++) x |= w[i];
+        if (x == 0) status_or(ws, item, ST_IDENTITY);
+    }
+    u32 h = 0;
+    for (u32 b = 0; b < d.nblocks; b++) {
+        u64 buf[21];
+        const u64* mask = ws.lanes + (size_t)(d.block_ofs + b) * 21;
+        for (int i = 0; i < 21; i++) buf[i] = mask[i];
+        while (h < d.nholes && ws.holes[d.hole_ofs + h].block == b) {
+            const TxHole& hole = ws.holes[d.hole_ofs + h];
+            u32 w[8]; load8(w, tx_src(ws, hole.src_kind, hole.src_idx, item));
+            for (u32 t = 0; t < hole.len; t++) {
+                u32 sb = hole.src_off + t, db = hole.off + t;
+                u64 byte = (w[sb >> 2] >> (8 * (sb & 3))) & 0xffu;
+                buf[db >> 3] ^= byte << (8 * (db & 7));
+            }
+            h++;
+        }
+        for (int i = 0; i < 21; i++) st[i] ^= buf[i];
+        keccak_f1600(st);
+    }
+    u32 x[16];
+    for (int i = 0; i < 8; i++) { x[2 * i] = (u32)st[i]; x[2 * i + 1] = (u32)(st[i] >> 32); }
+    sc c = sc_reduce512(x);
+    sc claimed = sc_from_words(field_ptr(ws, d.chal_field, item));
+    if (!sc_equal(c, claimed)) status_or(ws, item, ST_CHALLENGE);
+    if (ws.chal) store8(ws.chal + ((size_t)d.out_slot * ws.count + item) * 8, c.v);
+}
+
+// ---- setup (per issuer): constant tables --------------------------------------------------------------------------
+// entry (base b, multiple m in 1..128) of the radix-256 table: m*P in affine Niels form.
+AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words*/) {
+    ge p; u32 ok = ge_decompress(p, enc);
+    ge acc = ge_identity();
+    pniels pn = ge_to_pniels(p);
+    for (int bit = 7; bit >= 0; bit--) {
+        acc = ge_dbl(acc, true);
+        if ((m >> bit) & 1u) acc = ge_add_pn(acc, pn, true);
+    }
+    // 1/Z = Z^(p-2) = (Z^(2^252-3))^8 * Z^3 ... use pow_p58: Z^(p-2) = Z^(2^255-21) = (Z^(2^252-3))^(8) * Z^3
+    fe z = acc.Z;
+    fe t = fe_pow_p58(z);               // z^(2^252-3)
+    t = fe_sqn(t, 3);                   // z^(2^255-24)
+    fe zinv = fe_mul(t, fe_mul(fe_sq(z), z));  // * z^3 -> z^(2^255-21)
+    fe x = fe_mul(acc.X, zinv), y = fe_mul(acc.Y, zinv);
+    store_fe(out, fe_add(y, x));
+    store_fe(out + 8, fe_sub(y, x));
+    store_fe(out + 16, fe_mul(fe_mul(x, y), FE_D2()));
+    return ok;
+}
+
+}  // namespace afx

@@ -1,0 +1,375 @@
+// Host-side "shape compiler": turns an attribute-kind vector into the stage descriptors engine.cuh executes.
+//
+// It restates, as data, the statement structure of
+//   ProofOfValidCredential::verify   /root/reference/src/nizk/presentation.rs:324-443
+//   ProofOfEncryption::verify        /root/reference/src/nizk/encryption.rs:154-210
+//   ProofOfIssuance::verify          /root/reference/src/nizk/issuance.rs:132-218
+// and of the zkp 0.7 toolbox / merlin framing they drive: which points are allocated under which
+// labels and in which order, which constraints exist, and every quirk of SURVEY A.6 (compacted-index constraint loop,
+// G_y padded to >= 3, singular/plural transcript labels, identity rejection only for allocated points).
+// Pure byte/bookkeeping work: no field arithmetic happens on the host.
+#pragma once
+#include <array>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace afx {
+
+// ---- per-issuer constants -------------------------------------------------------------------------
+// Constant point ids follow the SystemParameters::to_bytes order (parameters.rs:155-184), then C_W, I.
+struct IssuerConsts {
+    u32 n = 0, ny = 0;
+    std::vector<std::array<uint8_t, 32>> enc;      // compressed encoding of constant point id
+    std::vector<std::array<uint8_t, 32>> enc_neg;  // compressed encoding of its negation (filled by device setup)
+    u32 id_G() const { return 0; }
+    u32 id_Gw() const { return 1; }
+    u32 id_Gwp() const { return 2; }
+    u32 id_Gx0() const { return 3; }
+    u32 id_Gx1() const { return 4; }
+    u32 id_Gy(u32 i) const { return 5 + i; }
+    u32 id_Gm(u32 i) const { return 5 + ny + i; }
+    u32 id_GV() const { return 5 + ny + n; }
+    u32 id_Ga() const { return 6 + ny + n; }
+    u32 id_Ga0() const { return 7 + ny + n; }
+    u32 id_Ga1() const { return 8 + ny + n; }
+    u32 id_CW() const { return 9 + ny + n; }
+    u32 id_I() const { return 10 + ny + n; }
+    u32 count() const { return 11 + ny + n; }
+};
+// secret rows (secdig / secsc): 0 = x_0, 1 = x_1, 2 + i = y_i, then w, w'
+inline u32 sec_x0() { return 0; }
+inline u32 sec_x1() { return 1; }
+inline u32 sec_y(u32 i) { return 2 + i; }
+
+inline size_t sysparams_size(u32 n) { return n < 3 ? 32 * (5 + 3 + n + 4) + 4 : 32 * (5 + 2 * n + 4) + 4; }  // parameters.rs:34-40
+inline size_t secret_size(u32 n) { return 32 * (5 + n) + 4; }                                                // amacs.rs:44-46
+
+// ---- transcript template builder (symbolic STROBE-128) ----------------------------------
+struct TxBuilder {
+    std::vector<std::array<uint8_t, 168>> blocks;
+    std::array<uint8_t, 168> cur{};
+    int pos = 0, pos_begin = 0, cur_flags = 0;
+    std::vector<TxHole> holes;
+    std::vector<TxIdCheck> ids;
+    bool init_done = false;
+
+    void run_f() {
+        cur[pos] ^= (uint8_t)pos_begin; cur[pos + 1] ^= 0x04; cur[167] ^= 0x80;
+        blocks.push_back(cur); cur.fill(0); pos = 0; pos_begin = 0;
+    }
+    void absorb(const uint8_t* d, size_t n) {
+        for (size_t i = 0; i < n; i++) { cur[pos++] ^= d[i]; if (pos == 166) run_f(); }
+    }
+    void absorb_hole(u32 kind, u32 idx) {
+        u32 done = 0;
+        while (done < 32) {
+            u32 room = 166 - pos, take = (32 - done) < room ? (32 - done) : room;
+            TxHole h; h.block = (u16)blocks.size(); h.off = (u16)pos; h.len = (u16)take; h.src_off = (u16)done; h.src_kind = (u16)kind; h.src_idx = (u16)idx;
+            holes.push_back(h);
+            pos += take; done += take;
+            if (pos == 166) run_f();
+        }
+    }
+    void begin_op(int flags, bool more) {
+        if (more) return;
+        uint8_t hdr[2] = {(uint8_t)pos_begin, (uint8_t)flags};
+        pos_begin = pos + 1; cur_flags = flags;
+        absorb(hdr, 2);
+        if ((flags & (4 | 32)) && pos != 0) run_f();
+    }
+    void meta_ad(const void* d, size_t n, bool more) { begin_op(16 | 2, more); absorb((const uint8_t*)d, n); }
+    void ad(const void* d, size_t n, bool more) { begin_op(2, more); absorb((const uint8_t*)d, n); }
+    void start(const char* transcript_label) {
+        // Strobe128::new("Merlin v1.0"): the initial permutation is a block whose mask is the 18 header bytes
+        static const uint8_t hdr[6] = {1, 168, 1, 0, 1, 96};
+        std::memcpy(cur.data(), hdr, 6); std::memcpy(cur.data() + 6, "STROBEv1.0.2", 12);
+        blocks.push_back(cur); cur.fill(0); pos = 0; pos_begin = 0;
+        meta_ad("Merlin v1.0", 11, false);
+        append_message("dom-sep", transcript_label, std::strlen(transcript_label));
+    }
+    void append_header(const char* label, u32 len) {
+        meta_ad(label, std::strlen(label), false);
+        uint8_t l4[4] = {(uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24)};
+        meta_ad(l4, 4, true);
+    }
+    void append_message(const char* label, const void* msg, size_t len) { append_header(label, (u32)len); ad(msg, len, false); }
+    // zkp TranscriptProtocol
+    void domain_sep(const char* label) {
+        append_message("dom-sep", "schnorrzkp/1.0/ristretto255", 27);
+        append_message("dom-sep", label, std::strlen(label));
+    }
+    void scalar_var(const char* label) { append_message("scvar", label, std::strlen(label)); }
+    void point_var_const(const char* label, const uint8_t enc[32]) {  // per-issuer constant: identity checked at ctx creation
+        append_message("ptvar", label, std::strlen(label)); append_message("val", enc, 32);
+    }
+    void point_var(const char* label, u32 kind, u32 idx) {  // validate_and_append_point_var
+        TxIdCheck c; c.src_kind = (u16)kind; c.src_idx = (u16)idx; ids.push_back(c);
+        append_message("ptvar", label, std::strlen(label));
+        append_header("val", 32); begin_op(2, false); absorb_hole(kind, idx);
+    }
+    void blinding_commitment(const char* label, u32 commit_slot) {
+        append_message("blindcom", label, std::strlen(label));
+        append_header("val", 32); begin_op(2, false); absorb_hole(SRC_COMMIT, commit_slot);
+    }
+    void challenge() {  // get_challenge("chal"): 64 bytes; the output is the head of the state after the last block
+        append_header("chal", 64);
+        int nb = (int)blocks.size();
+        begin_op(1 | 2 | 4, false);
+        if ((int)blocks.size() == nb) throw std::logic_error("transcript: prf did not close a block");
+        if (pos != 0) throw std::logic_error("transcript: dangling bytes");
+    }
+};
+
+// ---- compiled program --------------------------------------------------------------------------------
+struct ShapeProgram {
+    u32 n_fields = 0, n_tables = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
+    std::vector<u16> scalar_fields;
+    std::vector<PointJob> point_jobs;
+    bool has_amac = false;
+    AmacDesc amac{};
+    std::vector<MsmDesc> msms;
+    std::vector<TxDesc> txs;
+    std::vector<u64> lanes;
+    std::vector<TxHole> holes;
+    std::vector<TxIdCheck> ids;
+    u32 z_comp_slot = 0;          // where the recomputed Z encoding lands (debug dump)
+    std::vector<u32> dump_commit; // commit slots that are blinding commitments, in constraint order (debug dump)
+};
+
+inline ScalarSrc sc_field(u32 f) { ScalarSrc s; s.op = SC_FIELD; s.f0 = (u16)f; s.f1 = s.f2 = 0; return s; }
+inline ScalarSrc sc_mul2(u32 a, u32 b) { ScalarSrc s; s.op = SC_MUL; s.f0 = (u16)a; s.f1 = (u16)b; s.f2 = 0; return s; }
+inline ScalarSrc sc_muladd3(u32 a, u32 b, u32 c) { ScalarSrc s; s.op = SC_MULADD; s.f0 = (u16)a; s.f1 = (u16)b; s.f2 = (u16)c; return s; }
+
+struct MsmBuilder {
+    MsmDesc d{};
+    explicit MsmBuilder(u32 out_slot) { std::memset(&d, 0, sizeof d); d.out_slot = (u16)out_slot; }
+    void var(u32 table_slot, ScalarSrc s, bool neg = false) {
+        if (d.nvar >= MAX_VAR_TERMS) throw std::length_error("too many variable-base terms");
+        VarTerm& t = d.var[d.nvar++]; t.table_slot = (u16)table_slot; t.neg = neg; t.s = s;
+    }
+    void con(u32 ctab, ScalarSrc s, bool neg = false) {
+        if (d.ncon >= MAX_CONST_TERMS) throw std::length_error("too many constant-base terms");
+        ConstTerm& t = d.con[d.ncon++]; t.ctab = (u16)ctab; t.neg = neg; t.s = s;
+    }
+};
+
+// Fold the hole-free leading blocks into a midstate, append the rest to the program.
+inline void finish_transcript(ShapeProgram& P, TxBuilder& tb, u32 chal_field, u32 out_slot) {
+    TxDesc d; std::memset(&d, 0, sizeof d);
+    u32 first_hole_block = tb.holes.empty() ? (u32)tb.blocks.size() - 1 : tb.holes.front().block;
+    if (first_hole_block > tb.blocks.size() - 1) first_hole_block = (u32)tb.blocks.size() - 1;  // keep >= 1 block on the device
+    u64 st[25]; for (int i = 0; i < 25; i++) st[i] = 0;
+    for (u32 b = 0; b < first_hole_block; b++) {
+        for (int i = 0; i < 21; i++) { u64 lane; std::memcpy(&lane, tb.blocks[b].data() + 8 * i, 8); st[i] ^= lane; }
+        keccak_f1600(st);
+    }
+    for (int i = 0; i < 25; i++) d.midstate[i] = st[i];
+    d.block_ofs = (u32)(P.lanes.size() / 21);
+    d.nblocks = (u32)tb.blocks.size() - first_hole_block;
+    for (u32 b = first_hole_block; b < tb.blocks.size(); b++)
+        for (int i = 0; i < 21; i++) { u64 lane; std::memcpy(&lane, tb.blocks[b].data() + 8 * i, 8); P.lanes.push_back(lane); }
+    d.hole_ofs = (u32)P.holes.size(); d.nholes = (u32)tb.holes.size();
+    for (TxHole h : tb.holes) { h.block = (u16)(h.block - first_hole_block); P.holes.push_back(h); }
+    d.id_ofs = (u32)P.ids.size(); d.nid = (u32)tb.ids.size();
+    for (const TxIdCheck& c : tb.ids) P.ids.push_back(c);
+    d.chal_field = (u16)chal_field; d.out_slot = (u16)out_slot;
+    P.txs.push_back(d);
+}
+
+inline size_t presentation_num_fields(u32 n, const uint8_t* kinds) {
+    size_t hs = 0, r = 0, hp = 0;
+    for (u32 i = 0; i < n; i++) { hs += kinds[i] == 1; r += (kinds[i] == 0 || kinds[i] == 2); hp += kinds[i] == 3; }
+    return 1 + 3 + hs + 3 + n + r + 14 * hp;
+}
+
+// ProofOfValidCredential::verify as a program (presentation.rs:324-443).
+inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+    if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
+    for (u32 i = 0; i < n; i++) if (kinds[i] > 3) throw std::invalid_argument("bad attribute kind");
+    ShapeProgram P;
+    // ---- field map
+    u32 hs = 0; std::vector<int> ss_rank(n, -1);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 1) ss_rank[i] = (int)hs++;
+    u32 f = 0;
+    const u32 F_CHAL = f++; const u32 F_RESP = f; f += 3 + hs;
+    const u32 F_CX0 = f++, F_CX1 = f++, F_CV = f++; const u32 F_CY = f; f += n;
+    std::vector<int> F_REV(n, -1);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0 || kinds[i] == 2) F_REV[i] = (int)f++;
+    std::vector<u32> enc_base, enc_attr;
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 3) { enc_base.push_back(f); enc_attr.push_back(i); f += 14; }
+    P.n_fields = f;
+    P.scalar_fields.push_back((u16)F_CHAL);
+    for (u32 k = 0; k < 3 + hs; k++) P.scalar_fields.push_back((u16)(F_RESP + k));
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) P.scalar_fields.push_back((u16)F_REV[i]);
+    for (u32 b : enc_base) for (u32 k = 0; k < 7; k++) P.scalar_fields.push_back((u16)(b + k));
+
+    // ---- point jobs
+    u32 ntab = 0, next = 0, ncomp = 0;
+    auto job = [&](int fa, int fb, u32 op, bool table, bool ext, bool comp, bool compneg, int* tslot, int* eslot, int* cslot, int* cnslot) {
+        PointJob j; j.field_a = (int16_t)fa; j.field_b = (int16_t)fb; j.op = (u16)op; j.pad = 0;
+        j.table_slot = table ? (int16_t)ntab++ : -1; j.ext_slot = ext ? (int16_t)next++ : -1;
+        j.comp_slot = comp ? (int16_t)ncomp++ : -1; j.compneg_slot = compneg ? (int16_t)ncomp++ : -1;
+        if (tslot) *tslot = j.table_slot; if (eslot) *eslot = j.ext_slot; if (cslot) *cslot = j.comp_slot; if (cnslot) *cnslot = j.compneg_slot;
+        P.point_jobs.push_back(j);
+    };
+    int T_CX0, T_CX1, E_CV;
+    job((int)F_CX0, -1, PJ_COPY, true, false, false, false, &T_CX0, nullptr, nullptr, nullptr);
+    job((int)F_CX1, -1, PJ_COPY, true, false, false, false, &T_CX1, nullptr, nullptr, nullptr);
+    job((int)F_CV, -1, PJ_COPY, false, true, false, false, nullptr, &E_CV, nullptr, nullptr);
+    std::vector<int> T_CY(n, -1), T_X(n, -1);
+    for (u32 i = 0; i < n; i++) {
+        job((int)(F_CY + i), -1, PJ_COPY, true, false, false, false, &T_CY[i], nullptr, nullptr, nullptr);
+        if (kinds[i] == 2) job((int)(F_CY + i), F_REV[i], PJ_ADD, true, false, false, false, &T_X[i], nullptr, nullptr, nullptr);  // X_i = C_y[i] + M_i (:348)
+    }
+    struct EncSlots { int T_PK, T_E1, C_NEG_E1, T_CY2, T_CY3, T_CY2P, T_D, C_D; };
+    std::vector<EncSlots> es(enc_base.size());
+    for (size_t e = 0; e < enc_base.size(); e++) {
+        u32 b = enc_base[e];
+        job((int)(b + 7), -1, PJ_COPY, true, false, false, false, &es[e].T_PK, nullptr, nullptr, nullptr);
+        job((int)(b + 8), -1, PJ_COPY, true, false, false, true, &es[e].T_E1, nullptr, nullptr, &es[e].C_NEG_E1);  // E1 and compress(-E1) (encryption.rs:184-185)
+        job((int)(b + 11), -1, PJ_COPY, true, false, false, false, &es[e].T_CY2, nullptr, nullptr, nullptr);
+        job((int)(b + 12), -1, PJ_COPY, true, false, false, false, &es[e].T_CY3, nullptr, nullptr, nullptr);
+        job((int)(b + 13), -1, PJ_COPY, true, false, false, false, &es[e].T_CY2P, nullptr, nullptr, nullptr);
+        job((int)(b + 10), (int)(b + 9), PJ_SUB, true, false, true, false, &es[e].T_D, nullptr, &es[e].C_D, nullptr);  // C_y_1 - E2 (encryption.rs:183)
+    }
+    // ---- aMAC (presentation.rs:342-352)
+    P.has_amac = true;
+    AmacDesc& A = P.amac; std::memset(&A, 0, sizeof A);
+    A.ext_cv = (u16)E_CV;
+    A.var[A.nvar].table_slot = (u16)T_CX0; A.var[A.nvar++].digit_row = (u16)sec_x0();
+    A.var[A.nvar].table_slot = (u16)T_CX1; A.var[A.nvar++].digit_row = (u16)sec_x1();
+    for (u32 i = 0; i < n; i++) {
+        A.var[A.nvar].table_slot = (u16)(kinds[i] == 2 ? T_X[i] : T_CY[i]); A.var[A.nvar++].digit_row = (u16)sec_y(i);
+        if (kinds[i] == 0) { AmacPs& p = A.ps[A.nps++]; p.ctab = (u16)ic.id_Gm(i); p.y_row = (u16)sec_y(i); p.field_m = (u16)F_REV[i]; p.pad = 0; }  // (:346)
+    }
+    const u32 T_Z = ntab++; const u32 C_Z = ncomp++;
+    A.out_table_slot = (u16)T_Z; A.out_comp_slot = (u16)C_Z; P.z_comp_slot = C_Z;
+    P.n_tables = ntab; P.n_ext = next; P.n_comp = ncomp;
+
+    // ---- main proof: constraints (:416-433) and transcript (:355-412)
+    const ScalarSrc R_z = sc_field(F_RESP + 0), R_z0 = sc_field(F_RESP + 1), R_t = sc_field(F_RESP + 2), C_main = sc_field(F_CHAL);
+    std::vector<u32> nsp;  // original indices of the non-SecretPoint attributes (the compacted C_y list)
+    for (u32 i = 0; i < n; i++) if (kinds[i] != 3) nsp.push_back(i);
+    u32 slot = 0;
+    struct Con { u32 slot; const char* label; };
+    std::vector<Con> main_cons;
+    { MsmBuilder m(slot); m.con(ic.id_I(), R_z); m.var(T_Z, C_main, true); P.msms.push_back(m.d); main_cons.push_back({slot++, "Z"}); }
+    { MsmBuilder m(slot); m.var(T_CX0, R_t); m.con(ic.id_Gx0(), R_z0); m.con(ic.id_Gx1(), R_z); m.var(T_CX1, C_main, true);
+      P.msms.push_back(m.d); main_cons.push_back({slot++, "C_x_1"}); }
+    for (u32 i = 0; i < nsp.size(); i++) {  // compacted-index loop: i indexes kinds / G_y / G_m, nsp[i] is the commitment
+        if (kinds[i] == 3) continue;
+        MsmBuilder m(slot); m.con(ic.id_Gy(i), R_z);
+        if (kinds[i] == 1) m.con(ic.id_Gm(i), sc_field(F_RESP + 3 + ss_rank[i]));
+        m.var(T_CY[nsp[i]], C_main, true);
+        P.msms.push_back(m.d); main_cons.push_back({slot++, "C_y"});
+    }
+    {
+        TxBuilder tb; tb.start("2019/1416 anonymous credential"); tb.domain_sep("2019/1416 presentation proof");
+        tb.scalar_var("z"); tb.scalar_var("z_0"); tb.scalar_var("t");
+        for (u32 k = 0; k < hs; k++) tb.scalar_var("m");
+        tb.point_var_const("I", ic.enc[ic.id_I()].data());
+        tb.point_var("C_x_1", SRC_FIELD, F_CX1); tb.point_var("C_x_0", SRC_FIELD, F_CX0);
+        tb.point_var_const("G_x_0", ic.enc[ic.id_Gx0()].data()); tb.point_var_const("G_x_1", ic.enc[ic.id_Gx1()].data());
+        for (u32 i : nsp) tb.point_var("C_y", SRC_FIELD, F_CY + i);
+        for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("G_y", ic.enc[ic.id_Gy(i)].data());
+        for (u32 i = 0; i < n; i++) if (kinds[i] == 1) tb.point_var_const("G_m", ic.enc[ic.id_Gm(i)].data());
+        tb.point_var("Z", SRC_COMP, C_Z);
+        for (const Con& c : main_cons) { tb.blinding_commitment(c.label, c.slot); P.dump_commit.push_back(c.slot); }
+        tb.challenge();
+        finish_transcript(P, tb, F_CHAL, 0);
+    }
+    // ---- proofs of encryption (encryption.rs:154-210), one per hidden plaintext attribute (presentation.rs:438-440)
+    for (size_t e = 0; e < enc_base.size(); e++) {
+        u32 b = enc_base[e], idx = enc_attr[e];
+        const ScalarSrc c = sc_field(b), r_a = sc_field(b + 1), r_a0 = sc_field(b + 2), r_a1 = sc_field(b + 3), r_m3 = sc_field(b + 4),
+                        r_z = sc_field(b + 5), r_z1 = sc_field(b + 6);
+        u32 s_pk, s_d, s_c2p, s_e1, s_c3;
+        { MsmBuilder m(slot); m.con(ic.id_Ga(), r_a); m.con(ic.id_Ga0(), r_a0); m.con(ic.id_Ga1(), r_a1); m.var(es[e].T_PK, c, true); P.msms.push_back(m.d); s_pk = slot++; }
+        { MsmBuilder m(slot); m.con(ic.id_Gy(0), r_z); m.var(es[e].T_E1, r_a, true); m.var(es[e].T_D, c, true); P.msms.push_back(m.d); s_d = slot++; }
+        { MsmBuilder m(slot); m.var(es[e].T_CY2, r_a1); m.var(es[e].T_CY2P, c, true); P.msms.push_back(m.d); s_c2p = slot++; }
+        { MsmBuilder m(slot); m.var(es[e].T_CY2, r_a0); m.var(es[e].T_CY2P, r_m3); m.con(ic.id_Gy(1), r_z1); m.var(es[e].T_E1, c, true); P.msms.push_back(m.d); s_e1 = slot++; }
+        { MsmBuilder m(slot); m.con(ic.id_Gy(2), r_z); m.con(ic.id_Gm(idx), r_m3); m.var(es[e].T_CY3, c, true); P.msms.push_back(m.d); s_c3 = slot++; }
+        TxBuilder tb; tb.start("2019/1416 anonymous credentials"); tb.domain_sep("2019/1416 proof of encryption");
+        tb.scalar_var("a"); tb.scalar_var("a0"); tb.scalar_var("a1"); tb.scalar_var("m3"); tb.scalar_var("z"); tb.scalar_var("z1");
+        tb.point_var("pk", SRC_FIELD, b + 7);
+        tb.point_var_const("G_a", ic.enc[ic.id_Ga()].data()); tb.point_var_const("G_a_0", ic.enc[ic.id_Ga0()].data());
+        tb.point_var_const("G_a_1", ic.enc[ic.id_Ga1()].data());
+        tb.point_var_const("G_y_1", ic.enc[ic.id_Gy(0)].data()); tb.point_var_const("G_y_2", ic.enc[ic.id_Gy(1)].data());
+        tb.point_var_const("G_y_3", ic.enc[ic.id_Gy(2)].data()); tb.point_var_const("G_m_3", ic.enc[ic.id_Gm(idx)].data());
+        tb.point_var("C_y_2", SRC_FIELD, b + 11); tb.point_var("C_y_3", SRC_FIELD, b + 12); tb.point_var("C_y_2'", SRC_FIELD, b + 13);
+        tb.point_var("C_y_1-E2", SRC_COMP, (u32)es[e].C_D);
+        tb.point_var("E1", SRC_FIELD, b + 8);
+        tb.point_var("-E1", SRC_COMP, (u32)es[e].C_NEG_E1);
+        tb.blinding_commitment("pk", s_pk); tb.blinding_commitment("C_y_1-E2", s_d); tb.blinding_commitment("C_y_2'", s_c2p);
+        tb.blinding_commitment("E1", s_e1); tb.blinding_commitment("C_y_3", s_c3);
+        for (u32 s : {s_pk, s_d, s_c2p, s_e1, s_c3}) P.dump_commit.push_back(s);
+        tb.challenge();
+        finish_transcript(P, tb, b, (u32)(1 + e));
+    }
+    P.n_msm = slot; P.n_proofs = (u32)P.txs.size();
+    return P;
+}
+
+// CredentialIssuance::verify as a program (issuer.rs:48-57 -> issuance.rs:132-218).
+// kinds: 0 = scalar attribute (M_i = m_i * G_m[i]), 2 = point attribute.  Fields: attr[n], t, U, V, challenge, responses[n+5].
+inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+    if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
+    for (u32 i = 0; i < n; i++) if (kinds[i] != 0 && kinds[i] != 2) throw std::invalid_argument("bad request kind");
+    ShapeProgram P;
+    const u32 F_ATTR = 0, F_T = n, F_U = n + 1, F_V = n + 2, F_CHAL = n + 3, F_RESP = n + 4;
+    P.n_fields = 2 * n + 9;
+    // responses: w, w', x_0, x_1, y[n], 1  (issuance.rs:146-159)
+    const u32 R_w = F_RESP, R_wp = F_RESP + 1, R_x0 = F_RESP + 2, R_x1 = F_RESP + 3, R_y = F_RESP + 4, R_one = F_RESP + 4 + n;
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) P.scalar_fields.push_back((u16)(F_ATTR + i));
+    P.scalar_fields.push_back((u16)F_T); P.scalar_fields.push_back((u16)F_CHAL);
+    for (u32 k = 0; k < n + 5; k++) P.scalar_fields.push_back((u16)(F_RESP + k));
+    u32 ntab = 0;
+    auto table_job = [&](u32 field) { PointJob j; j.field_a = (int16_t)field; j.field_b = -1; j.op = PJ_COPY; j.pad = 0; j.table_slot = (int16_t)ntab; j.ext_slot = -1;
+                                      j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j); return ntab++; };
+    const u32 T_U = table_job(F_U), T_V = table_job(F_V);
+    std::vector<int> T_M(n, -1);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 2) T_M[i] = (int)table_job(F_ATTR + i);
+    P.n_tables = ntab; P.n_ext = 0; P.n_comp = 0;
+    const ScalarSrc c = sc_field(F_CHAL);
+    u32 slot = 0;
+    // derived allocated points that are not inputs: tU = t*U (:180) and M_i = m_i * G_m[i] for scalar attributes (:184)
+    u32 S_tU; { MsmBuilder m(slot); m.var(T_U, sc_field(F_T)); P.msms.push_back(m.d); S_tU = slot++; }
+    std::vector<int> S_M(n, -1);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) { MsmBuilder m(slot); m.con(ic.id_Gm(i), sc_field(F_ATTR + i)); P.msms.push_back(m.d); S_M[i] = (int)slot++; }
+    // constraints (:195-215)
+    u32 S_CW, S_I, S_V;
+    { MsmBuilder m(slot); m.con(ic.id_Gw(), sc_field(R_w)); m.con(ic.id_Gwp(), sc_field(R_wp)); m.con(ic.id_CW(), c, true); P.msms.push_back(m.d); S_CW = slot++; }
+    { MsmBuilder m(slot); m.con(ic.id_GV(), sc_field(R_one)); m.con(ic.id_Gx0(), sc_field(R_x0), true); m.con(ic.id_Gx1(), sc_field(R_x1), true);
+      for (u32 i = 0; i < n; i++) m.con(ic.id_Gy(i), sc_field(R_y + i), true);
+      m.con(ic.id_I(), c, true); P.msms.push_back(m.d); S_I = slot++; }
+    { MsmBuilder m(slot); m.con(ic.id_Gw(), sc_field(R_w));
+      m.var(T_U, sc_muladd3(R_x0, R_x1, F_T));               // x_0*U + x_1*(t*U) = (x_0 + x_1*t)*U
+      for (u32 i = 0; i < n; i++) {
+          if (kinds[i] == 0) m.con(ic.id_Gm(i), sc_mul2(R_y + i, F_ATTR + i));  // y_i * (m_i*G_m[i])
+          else m.var((u32)T_M[i], sc_field(R_y + i));
+      }
+      m.var(T_V, c, true); P.msms.push_back(m.d); S_V = slot++; }
+    TxBuilder tb; tb.start("2019/1416 anonymous credential"); tb.domain_sep("2019/1416 issuance proof");
+    tb.scalar_var("w"); tb.scalar_var("w'"); tb.scalar_var("x_0"); tb.scalar_var("x_1");
+    for (u32 i = 0; i < n; i++) tb.scalar_var("y");
+    tb.scalar_var("1");
+    tb.point_var_const("G_V", ic.enc[ic.id_GV()].data()); tb.point_var_const("G_w", ic.enc[ic.id_Gw()].data());
+    tb.point_var_const("G_w_prime", ic.enc[ic.id_Gwp()].data());
+    tb.point_var_const("-G_x_0", ic.enc_neg[ic.id_Gx0()].data()); tb.point_var_const("-G_x_1", ic.enc_neg[ic.id_Gx1()].data());
+    for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("-G_y", ic.enc_neg[ic.id_Gy(i)].data());
+    tb.point_var_const("C_W", ic.enc[ic.id_CW()].data()); tb.point_var_const("I", ic.enc[ic.id_I()].data());
+    tb.point_var("U", SRC_FIELD, F_U); tb.point_var("V", SRC_FIELD, F_V); tb.point_var("tU", SRC_COMMIT, S_tU);
+    for (u32 i = 0; i < n; i++) { if (kinds[i] == 0) tb.point_var("M", SRC_COMMIT, (u32)S_M[i]); else tb.point_var("M", SRC_FIELD, F_ATTR + i); }
+    tb.blinding_commitment("C_W", S_CW); tb.blinding_commitment("I", S_I); tb.blinding_commitment("V", S_V);
+    for (u32 s : {S_CW, S_I, S_V}) P.dump_commit.push_back(s);
+    tb.challenge();
+    finish_transcript(P, tb, F_CHAL, 0);
+    P.n_msm = slot; P.n_proofs = 1;
+    return P;
+}
+
+}  // namespace afx

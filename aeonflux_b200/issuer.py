@@ -1,0 +1,120 @@
+"""Host-side mirror of the reference's interface for the hot path (/root/reference/src/issuer.rs), batch form.
+
+    reference (Rust)                                      here
+    ----------------------------------------------------  ----------------------------------------------------
+    Issuer { system_parameters, issuer_parameters,        Issuer(system_parameters, issuer_parameters, amacs_key)
+             amacs_key }                 issuer.rs:61-65    -- the same to_bytes() encodings (parameters.rs:155-184,
+                                                               C_W||I, amacs.rs:110-125)
+    Issuer::verify(&self, &presentation) issuer.rs:141-147  Issuer.verify_batch(PresentationBatch) -> verdicts
+    CredentialIssuance::verify(self, &sp, &ip)              Issuer.verify_issuance_batch(IssuanceBatch) -> verdicts
+                                         issuer.rs:48-57      (amacs_key=None suffices: it is the user-side check)
+    Result<(), CredentialError::VerificationFailure>        verdict 0 / 1 per item (errors.rs:152-156)
+
+The reference defines no wire format for presentations or issuances (presentation.rs:117 "XXX"); the flat
+struct-of-arrays layout is documented in include/aeonflux_b200.h.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _binding as B
+
+KIND_PUBLIC_SCALAR, KIND_SECRET_SCALAR, KIND_PUBLIC_POINT, KIND_SECRET_POINT = 0, 1, 2, 3
+
+
+class PresentationBatch:
+    """kinds: bytes of AFX_KIND_*, one per attribute; fields: uint8 array [n_fields][count][32]."""
+
+    def __init__(self, kinds, fields):
+        self.kinds = bytes(kinds)
+        self.fields = np.ascontiguousarray(fields, dtype=np.uint8)
+        if self.fields.ndim != 3 or self.fields.shape[2] != 32:
+            raise ValueError("fields must be [n_fields][count][32] bytes")
+
+    @property
+    def count(self):
+        return self.fields.shape[1]
+
+    @staticmethod
+    def from_items(kinds, items):
+        """items: uint8 [count][n_fields][32] (item-major, as a list of per-presentation word lists)."""
+        return PresentationBatch(kinds, np.ascontiguousarray(np.asarray(items, dtype=np.uint8).transpose(1, 0, 2)))
+
+
+IssuanceBatch = PresentationBatch   # same container; kinds are 0 (scalar attribute) / 2 (point attribute)
+
+
+class Issuer:
+    """An anonymous credential issuer/verifier bound to one B200 (issuer.rs:61-65)."""
+
+    def __init__(self, system_parameters: bytes, issuer_parameters: bytes, amacs_key: bytes = None, device: int = 0,
+                 max_batch: int = 65536, _binding=None):
+        if _binding is None:
+            from ._lib import load
+            _binding = load()
+        self._b = _binding
+        self.system_parameters = bytes(system_parameters)
+        self.issuer_parameters = bytes(issuer_parameters)
+        self.number_of_attributes = int.from_bytes(self.system_parameters[:4], "little")
+        self.max_batch = max_batch
+        if len(self.issuer_parameters) != 64:
+            raise ValueError("issuer_parameters must be C_W || I (64 bytes)")
+        h = ctypes.c_void_p()
+        sp = ctypes.create_string_buffer(self.system_parameters, len(self.system_parameters))
+        ip = ctypes.create_string_buffer(self.issuer_parameters, 64)
+        sk = ctypes.create_string_buffer(bytes(amacs_key), len(amacs_key)) if amacs_key is not None else None
+        rc = self._b.L.afx_ctx_create(ctypes.addressof(sp), len(self.system_parameters), ctypes.addressof(ip),
+                                      ctypes.addressof(sk) if sk is not None else None, len(amacs_key) if amacs_key is not None else 0,
+                                      device, max_batch, ctypes.byref(h))
+        if sk is not None:
+            ctypes.memset(sk, 0, len(amacs_key))
+        self._b.check(rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._b.L.afx_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- shape helpers
+    def num_fields(self, kinds):
+        return self._b.L.afx_presentation_num_fields(len(kinds), bytes(kinds))
+
+    def num_commitments(self, kinds):
+        return self._b.L.afx_presentation_num_commitments(len(kinds), bytes(kinds))
+
+    def num_proofs(self, kinds):
+        return self._b.L.afx_presentation_num_proofs(len(kinds), bytes(kinds))
+
+    @property
+    def launch_count(self):
+        return int(self._b.L.afx_launch_count(self._h))
+
+    def _run(self, fn, batch, ncommit, nproofs, debug):
+        count = batch.count
+        ptrs, keep = B._as_fields(batch.fields)
+        cb = B.afx_presentation_batch(len(batch.kinds), batch.kinds, count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        verdicts = np.zeros(count, np.uint8)
+        dbg = None
+        out = None
+        if debug:
+            out = {"Z": np.zeros((count, 32), np.uint8), "commitments": np.zeros((ncommit, count, 32), np.uint8),
+                   "challenges": np.zeros((nproofs, count, 32), np.uint8), "status": np.zeros(count, np.uint32)}
+            dbg = B.afx_debug_dump(out["Z"].ctypes.data, out["commitments"].ctypes.data, out["challenges"].ctypes.data, out["status"].ctypes.data)
+        rc = fn(self._h, ctypes.byref(cb), verdicts.ctypes.data, ctypes.byref(dbg) if dbg is not None else None)
+        self._b.check(rc)
+        return (verdicts, out) if debug else verdicts
+
+    def verify_batch(self, batch: PresentationBatch, debug=False):
+        """Batch Issuer::verify (issuer.rs:141-147): verdict 0 = Ok(()), 1 = Err(VerificationFailure)."""
+        return self._run(self._b.L.afx_verify_presentations, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
+
+    def verify_issuance_batch(self, batch: IssuanceBatch, debug=False):
+        """Batch CredentialIssuance::verify (issuer.rs:48-57)."""
+        return self._run(self._b.L.afx_verify_issuances, batch, 3, 1, debug)
+
+    def verify_batch_device(self, kinds, count, fields_dev_ptr, verdicts_dev_ptr, stream=0):
+        """Enqueue Issuer::verify for a batch already in device memory ([n_fields][count][32]); no synchronisation."""
+        self._b.check(self._b.L.afx_verify_presentations_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, verdicts_dev_ptr, stream))

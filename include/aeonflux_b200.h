@@ -1,0 +1,113 @@
+/* aeonflux_b200 -- C ABI of the B200 batch engine for aeonflux's issuer hot path.
+ *
+ * The reference (isislovecruft/aeonflux, Rust) has no FFI layer; its boundary for this path is the method surface
+ *     Issuer::verify(&self, &ProofOfValidCredential)            src/issuer.rs:141-147
+ *     Issuer::issue(&self, CredentialRequest, &mut rng)         src/issuer.rs:111-124
+ *     CredentialIssuance::verify(self, &SystemParameters, &IssuerParameters)   src/issuer.rs:48-57
+ * A batch entry point added beside each of those (Issuer::verify_batch, Issuer::issue_batch,
+ * CredentialIssuance::verify_batch -- see INTEGRATION.md for the Rust shim) flattens its arguments to the plain
+ * buffers below and binds exactly these symbols.  Plain pointers and sizes only; the caller owns every buffer; the
+ * library copies what it keeps.  All functions are synchronous unless they take a stream.
+ *
+ * Batch data is struct-of-arrays: "field f" is an array [count][32 bytes].  A 32-byte word is either a canonical
+ * little-endian Scalar or a CompressedRistretto -- the same encodings the reference's to_bytes() methods emit
+ * (src/parameters.rs:155-184, src/amacs.rs:110-125).
+ *
+ * Presentation fields for attribute kinds k[0..n) (0 = revealed scalar, 1 = hidden scalar, 2 = revealed point,
+ * 3 = hidden/encrypted point), h_s = #hidden scalars:
+ *     challenge, responses[3 + h_s], C_x_0, C_x_1, C_V, C_y[n],
+ *     revealed value of each kind-0 / kind-2 attribute in index order,
+ *     then per kind-3 attribute in index order: enc_challenge, enc_responses[6], pk, E1, E2, C_y_1, C_y_2, C_y_3, C_y_2'
+ * (struct fields of ProofOfValidCredential, src/nizk/presentation.rs:118-127, and ProofOfEncryption,
+ *  src/nizk/encryption.rs:32-41; hidden_scalar_indices and the enc proofs' indices are implied by kinds).
+ *
+ * Issuance fields for request kinds k[0..n) (0 = scalar attribute, 2 = point attribute -- a revealed point or the M1 of a
+ * plaintext, src/amacs.rs:224-244):
+ *     attribute[n], t, U, V, challenge, responses[n + 5]
+ * (CredentialIssuance = ProofOfIssuance(CompactProof) + AnonymousCredential{amac:{t,U,V}, attributes}, src/issuer.rs:42-45).
+ *
+ * Verdicts: 0 = Ok(()), 1 = Err(CredentialError::VerificationFailure) -- the only error these verify paths can return
+ * (src/errors.rs:152-156).  Byte strings the Rust types could never hold (undecodable point, scalar >= l) also give 1.
+ */
+#ifndef AEONFLUX_B200_H
+#define AEONFLUX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct afx_ctx afx_ctx;
+
+enum { AFX_OK = 0, AFX_ERR_ARG = -1, AFX_ERR_ENCODING = -2, AFX_ERR_CUDA = -3, AFX_ERR_ALLOC = -4, AFX_ERR_SHAPE = -5, AFX_ERR_NO_SECRET = -6 };
+enum { AFX_KIND_PUBLIC_SCALAR = 0, AFX_KIND_SECRET_SCALAR = 1, AFX_KIND_PUBLIC_POINT = 2, AFX_KIND_SECRET_POINT = 3 };
+
+/* Replaces Issuer::from_bytes / holding an `Issuer` (src/issuer.rs:61-65,152-159).
+ *   sysparams  = SystemParameters::to_bytes()   (src/parameters.rs:155-184)
+ *   issuer_pub = C_W || I                        (the 64 bytes src/issuer.rs:155,163 reserve for IssuerParameters)
+ *   secret     = amacs::SecretKey::to_bytes()    (src/amacs.rs:110-125); NULL for a user-side context that only runs
+ *                afx_verify_issuances
+ *   device     = CUDA device ordinal
+ * Validates every encoding (AFX_ERR_ENCODING), builds the per-issuer constant tables and transcript midstates on the
+ * device.  max_batch = largest `count` a single call will be given (workspace is sized for it). */
+int afx_ctx_create(const uint8_t* sysparams, size_t sysparams_len, const uint8_t issuer_pub[64], const uint8_t* secret,
+                   size_t secret_len, int device, size_t max_batch, afx_ctx** out);
+
+/* Drop for Issuer: zeroizes host and device copies of the secret key (src/amacs.rs:64-82) and frees everything. */
+void afx_ctx_destroy(afx_ctx* ctx);
+
+typedef struct {
+    uint16_t n_attrs;
+    const uint8_t* kinds;          /* [n_attrs] AFX_KIND_* ; identical for all items of the call */
+    size_t count;
+    const uint8_t* const* fields;  /* [n_fields] pointers, each to [count][32] bytes */
+    size_t n_fields;               /* must equal afx_presentation_num_fields(n_attrs, kinds) */
+} afx_presentation_batch;
+
+typedef struct {                   /* optional parity hooks (debug-transcript equivalent) */
+    uint8_t* Z;                    /* [count][32]              recomputed Z, compressed; nullable */
+    uint8_t* commitments;          /* [n_commitments][count][32] recomputed blinding commitments, constraint order; nullable */
+    uint8_t* challenges;           /* [n_proofs][count][32]    recomputed challenge scalars; nullable */
+    uint32_t* status;              /* [count] internal failure bits (1 bad point, 2 bad scalar, 4 identity, 8 challenge); nullable */
+} afx_debug_dump;
+
+size_t afx_presentation_num_fields(uint16_t n_attrs, const uint8_t* kinds);
+size_t afx_presentation_num_commitments(uint16_t n_attrs, const uint8_t* kinds);
+size_t afx_presentation_num_proofs(uint16_t n_attrs, const uint8_t* kinds);
+
+/* Batch Issuer::verify (src/issuer.rs:141-147).  Host buffers in, host verdicts out. */
+int afx_verify_presentations(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
+
+/* Same, with the batch already resident on the context's device: fields_dev = [n_fields][count][32] contiguous device
+ * memory, verdicts_dev = [count] device bytes; enqueued on `stream` (a cudaStream_t; NULL = default stream) without
+ * synchronizing.  This is what bench.py times for the kernel-only figure. */
+int afx_verify_presentations_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev,
+                                    void* verdicts_dev, void* stream);
+
+typedef struct {
+    uint16_t n_attrs;
+    const uint8_t* kinds;          /* [n_attrs] 0 = scalar attribute, 2 = point attribute */
+    size_t count;
+    const uint8_t* const* fields;  /* [2*n_attrs + 9] pointers: attribute[n], t, U, V, challenge, responses[n+5] */
+    size_t n_fields;
+} afx_issuance_batch;
+
+/* Batch CredentialIssuance::verify (src/issuer.rs:48-57 -> src/nizk/issuance.rs:132-218).  Needs no secret key. */
+int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
+
+/* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */
+uint64_t afx_launch_count(const afx_ctx* ctx);
+
+/* Device time of the most recent *_device / host call's kernel sequence is measured by the caller with events on the
+ * stream it passed; this returns the ordinal of the CUDA device the context lives on. */
+int afx_ctx_device(const afx_ctx* ctx);
+
+const char* afx_strerror(int code);
+const char* afx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

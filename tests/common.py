@@ -1,0 +1,85 @@
+"""Shared helpers for the parity tests: golden fixtures, oracle batches, trace comparison."""
+import json
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_SHAPES = ["readme4", "s16", "revealed10", "plain1_hidden", "scalar1", "quirk_sp_first", "quirk_sp_middle"]
+REQ = {"PS": ord("S"), "PP": ord("P"), "EP": ord("E")}
+
+
+def load_golden(name):
+    return json.load(open(os.path.join(GOLD, name + ".json")))
+
+
+def words(hexes):
+    return np.frombuffer(b"".join(bytes.fromhex(h) for h in hexes), np.uint8).reshape(len(hexes), 32).copy()
+
+
+def compare_with_oracle_trace(verdicts, dbg, overdicts, otrace):
+    """Engine debug dump vs the oracle's trace.  The reference returns at the first failing `?`, so the oracle trace is
+    only filled that far (all-zero rows beyond); everything it did compute must match bit for bit."""
+    assert (np.asarray(verdicts) == np.asarray(overdicts)).all(), (verdicts, overdicts)
+    count = len(verdicts)
+    cm = dbg["commitments"].transpose(1, 0, 2)
+    ch = dbg["challenges"].transpose(1, 0, 2)
+    for i in range(count):
+        if "Z" in otrace and otrace["Z"][i].any():
+            assert (dbg["Z"][i] == otrace["Z"][i]).all(), ("Z", i)
+        for k in range(otrace["commitments"].shape[1]):
+            if otrace["commitments"][i, k].any():
+                assert (cm[i, k] == otrace["commitments"][i, k]).all(), ("commitment", i, k)
+        for k in range(otrace["challenges"].shape[1]):
+            if otrace["challenges"][i, k].any():
+                assert (ch[i, k] == otrace["challenges"][i, k]).all(), ("challenge", i, k)
+
+
+CORRUPTIONS = ("response+1", "challenge+1", "C_x_0+B", "C_V+B", "revealed_scalar", "enc_E2+B", "enc_response+1",
+               "undecodable_point", "noncanonical_scalar", "identity_point")
+
+
+def corrupt_batch(pres, kinds, rng, fraction, oracle_points):
+    """Corrupt ~fraction of the items of pres [count][W][32] in place with the SURVEY 8d classes (byte-level versions:
+    adding B to a point is replaced by swapping in another valid point).  Returns the indices touched."""
+    from oracle import coracle as C
+    kinds = list(kinds)
+    n = len(kinds)
+    h_s = sum(k == C.KIND_SS for k in kinds)
+    enc0 = 7 + h_s + n + sum(k in (C.KIND_PS, C.KIND_PP) for k in kinds)
+    has_enc = any(k == C.KIND_SP for k in kinds)
+    ps = [i for i, k in enumerate(kinds) if k == C.KIND_PS]
+    count = pres.shape[0]
+    L = 2**252 + 27742317777372353535851937790883648493
+    idx = np.where(rng.random(count) < fraction)[0]
+    for j, i in enumerate(idx):
+        cls = CORRUPTIONS[j % len(CORRUPTIONS)]
+        def sc_plus1(w):
+            v = (int.from_bytes(pres[i, w].tobytes(), "little") + 1) % L
+            pres[i, w] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+        other = oracle_points[rng.integers(len(oracle_points))]
+        if cls == "response+1":
+            sc_plus1(1)
+        elif cls == "challenge+1":
+            sc_plus1(0)
+        elif cls == "C_x_0+B":
+            pres[i, 4 + h_s] = other
+        elif cls == "C_V+B":
+            pres[i, 6 + h_s] = other
+        elif cls == "revealed_scalar" and ps:
+            rev = 7 + h_s + n + sum(1 for k in kinds[:ps[0]] if k in (C.KIND_PS, C.KIND_PP))
+            sc_plus1(rev)
+        elif cls == "enc_E2+B" and has_enc:
+            pres[i, enc0 + 9] = other
+        elif cls == "enc_response+1" and has_enc:
+            sc_plus1(enc0 + 1)
+        elif cls == "undecodable_point":
+            pres[i, 5 + h_s] = np.frombuffer(bytes([3]) + bytes(31), np.uint8)   # odd => negative => invalid encoding
+        elif cls == "noncanonical_scalar":
+            v = int.from_bytes(pres[i, 2].tobytes(), "little") + L
+            pres[i, 2] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+        elif cls == "identity_point":
+            pres[i, 7 + h_s] = 0                                                   # C_y[0] := identity encoding
+        else:
+            sc_plus1(1)
+    return idx

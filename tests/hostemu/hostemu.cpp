@@ -1,0 +1,63 @@
+// TEST-ONLY host emulation of the engine: compiles the same __host__ __device__ stage bodies (engine.cuh) and the same
+// C-ABI implementation (api_impl.inc) with plain loops in place of CUDA kernels, so the shape compiler, the marshaling
+// and the stage logic can be debugged against the oracle on a machine without a GPU.  It is built by tests/ only, is
+// never loaded by the aeonflux_b200 package, and exercises none of the PTX paths -- GPU parity is proven separately by
+// the -m gpu tests through the real library.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../aeonflux_b200/csrc/engine.cuh"
+
+using namespace afx;
+typedef void* be_stream;
+#define AFX_BACKEND_NAME "host-emulation (tests only)"
+
+static int be_set_device(int) { return 0; }
+static int be_malloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 16); return *p == nullptr; }
+static void be_free(void* p) { std::free(p); }
+static int be_h2d(void* d, const void* h, size_t n, be_stream) { std::memcpy(d, h, n); return 0; }
+static int be_d2h(void* h, const void* d, size_t n, be_stream) { std::memcpy(h, d, n); return 0; }
+static int be_memset(void* d, int v, size_t n, be_stream) { std::memset(d, v, n); return 0; }
+static int be_sync(be_stream) { return 0; }
+static int be_check_launch() { return 0; }
+
+static void be_launch_scalar_check(const Workspace& ws, const u16* f, u32 nf, be_stream) {
+    for (u32 k = 0; k < nf; k++) for (u32 i = 0; i < ws.count; i++) scalar_check_job(ws, f[k], i);
+}
+static void be_launch_points(const Workspace& ws, const PointJob* jobs, u32 nj, be_stream) {
+    for (u32 k = 0; k < nj; k++) for (u32 i = 0; i < ws.count; i++) points_job(ws, jobs[k], i);
+}
+static void be_launch_amac(const Workspace& ws, const AmacDesc* d, u32 nps, be_stream) {
+    std::vector<u32> scratch((size_t)(nps ? nps : 1) * 8);
+    for (u32 i = 0; i < ws.count; i++) amac_job(ws, *d, i, scratch.data(), 1);
+}
+static void be_launch_msm(const Workspace& ws, const MsmDesc* msms, const u32* idx, u32 nidx, u32 max_terms, u32, be_stream) {
+    std::vector<u32> scratch((size_t)max_terms * 8);
+    for (u32 k = 0; k < nidx; k++) {
+        const MsmDesc& d = msms[idx[k]];
+        CtabResolver r{nullptr, ws.ctabs, &d, 0};
+        for (u32 i = 0; i < ws.count; i++) msm_job(ws, d, i, scratch.data(), 1, r);
+    }
+}
+static void be_launch_transcript(const Workspace& ws, const TxDesc* txs, u32 ntx, be_stream) {
+    for (u32 k = 0; k < ntx; k++) for (u32 i = 0; i < ws.count; i++) transcript_job(ws, txs[k], i);
+}
+static void be_launch_verdict(const Workspace& ws, uint8_t* v, be_stream) { for (u32 i = 0; i < ws.count; i++) v[i] = ws.status[i] != 0; }
+static void be_launch_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encneg, u32* bad, be_stream) {
+    for (u32 b = 0; b < ncp; b++) {
+        for (u32 m = 1; m <= CTAB_ENTRIES; m++) {
+            u32 ok = ctab_entry_job(enc + 8 * b, m, ctabs + ((size_t)b * CTAB_ENTRIES + (m - 1)) * 24);
+            if (!ok) *bad |= 1;
+        }
+        ge p; ge_decompress(p, enc + 8 * b); ge_compress(encneg + 8 * b, ge_neg(p));
+    }
+}
+static void be_launch_secret_setup(const u32* secsc, u32 nsec, u32* secdig, const u32* Wenc, u32* W, u32* bad, be_stream) {
+    for (u32 t = 0; t < nsec; t++) { sc s = sc_from_words(secsc + 8 * t); if (!sc_is_canonical(s)) *bad |= 2; sc_recode16(secdig + 8 * t, s); }
+    ge p; if (!ge_decompress(p, Wenc)) *bad |= 1;
+    store_pniels(W, ge_to_pniels(p));
+}
+
+#include "../../aeonflux_b200/csrc/api_impl.inc"

@@ -1,0 +1,151 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle -- bit-exact compressed
+points (Z, every recomputed commitment), challenge scalars and verdicts, including deliberately corrupted proofs."""
+import numpy as np
+import pytest
+
+from tests.common import GOLDEN_SHAPES, REQ, compare_with_oracle_trace, corrupt_batch, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def readme4(coracle):
+    from aeonflux_b200 import Issuer
+    sp, ip, sk = coracle.make_issuer(4)
+    return coracle.Issuer(sp, ip, sk), Issuer(sp, ip, sk, device=0, max_batch=8192), (sp, ip, sk)
+
+
+def test_cuda_library_is_the_path_under_test():
+    from aeonflux_b200._lib import load
+    assert "cuda sm_100a" in load().version()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SHAPES)
+def test_golden_shapes(coracle, name):
+    from aeonflux_b200 import Issuer, PresentationBatch
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    orc = coracle.Issuer(sp, ip, sk)
+    rk = bytes(REQ[k] for k in g["request"])
+    count = 70                                                  # ragged: not a multiple of the 128-thread CTA
+    kinds, pres, issu = orc.synth(rk, g["hide"], g["config"].encode(), 0, count)
+    pres[1, 1, 3] ^= 0x10
+    pres[3, 0, 0] ^= 1
+    iss = Issuer(sp, ip, sk, device=0, max_batch=64)           # 64 < 70: two chunks
+    v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    compare_with_oracle_trace(v, dbg, ov, tr)
+    e = g["items"][0]                                           # committed fixture from the Python big-int oracle
+    assert dbg["Z"][0].tobytes().hex() == e["Z"]
+    assert dbg["commitments"][:len(e["commitments"]), 0].tobytes().hex() == "".join(e["commitments"])   # filled as far as the reference gets
+    assert dbg["challenges"][:len(e["challenges"]), 0].tobytes().hex() == "".join(e["challenges"])
+    assert v[0] == e["verdict"]
+    for c in e["corrupted"]:
+        from tests.common import words
+        w = words(c["words"])[None]
+        v1, d1 = iss.verify_batch(PresentationBatch.from_items(kinds, w), debug=True)
+        assert v1[0] == c["verdict"] == 1, c["class"]
+        ncm = len(c["commitments"])
+        assert d1["commitments"][:ncm, 0].tobytes().hex() == "".join(c["commitments"]), c["class"]
+    ik = bytes(e["issuance_kinds"])
+    issu[2, len(ik) + 1, 5] ^= 2
+    vi, dbgi = iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu), debug=True)
+    ovi, _, tri = orc.verify_issuances(ik, issu, trace=True)
+    compare_with_oracle_trace(vi, dbgi, ovi, tri)
+    assert dbgi["commitments"][:, 0].tobytes().hex() == "".join(e["issuance_commitments"])
+
+
+def test_readme4_batch_with_corruptions(readme4):
+    from aeonflux_b200 import PresentationBatch
+    orc, iss, _ = readme4
+    count = 4096 + 37
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"readme4", 1000, count, want_issuances=False)
+    rng = np.random.default_rng(1)
+    pts = pres[:64, 5:8].reshape(-1, 32).copy()
+    idx = corrupt_batch(pres, kinds, rng, 0.05, pts)
+    v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    compare_with_oracle_trace(v, dbg, ov, tr)
+    assert ov[idx].all() and int(ov.sum()) == len(idx)
+
+
+def test_s16_batch_with_corruptions(coracle):
+    from aeonflux_b200 import Issuer, PresentationBatch
+    sp, ip, sk = coracle.make_issuer(16)
+    orc = coracle.Issuer(sp, ip, sk)
+    count = 300
+    kinds, pres, issu = orc.synth(b"SSSSSSPP" + b"E" * 8, [0, 1] + list(range(8, 16)), b"s16", 0, count)
+    rng = np.random.default_rng(2)
+    pts = pres[:8, 6:9].reshape(-1, 32).copy()
+    idx = corrupt_batch(pres, kinds, rng, 0.1, pts)
+    iss = Issuer(sp, ip, sk, device=0, max_batch=512)
+    v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    compare_with_oracle_trace(v, dbg, ov, tr)
+    assert int(ov.sum()) == len(idx)
+    ik = bytes([0] * 6 + [2] * 10)
+    vi, dbgi = iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu), debug=True)
+    ovi, _, tri = orc.verify_issuances(ik, issu, trace=True)
+    compare_with_oracle_trace(vi, dbgi, ovi, tri)
+    assert not ovi.any()
+
+
+def test_edges(readme4):
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from aeonflux_b200._binding import AfxError
+    orc, iss, (sp, ip, sk) = readme4
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"edges", 0, 3)
+    assert len(iss.verify_batch(PresentationBatch(kinds, np.zeros((28, 0, 32), np.uint8)))) == 0
+    one = iss.verify_batch(PresentationBatch.from_items(kinds, pres[:1]))
+    assert list(one) == [0]
+    zeros = iss.verify_batch(PresentationBatch(kinds, np.zeros((28, 5, 32), np.uint8)))     # all-identity / all-zero input
+    assert zeros.all()
+    ones = iss.verify_batch(PresentationBatch(kinds, np.full((28, 5, 32), 0xff, np.uint8)))  # nothing decodes
+    assert ones.all()
+    with pytest.raises(AfxError):
+        iss.verify_batch(PresentationBatch(kinds, np.zeros((27, 2, 32), np.uint8)))
+    user = Issuer(sp, ip, None, device=0, max_batch=16)
+    with pytest.raises(AfxError):
+        user.verify_batch(PresentationBatch.from_items(kinds, pres))
+    assert not user.verify_issuance_batch(PresentationBatch.from_items(bytes([0, 0, 2, 2]), issu)).any()
+
+
+def test_device_resident_entry_point(readme4):
+    """afx_verify_presentations_device: inputs already in HBM, enqueued on the caller's stream (what bench.py times)."""
+    import torch
+    orc, iss, _ = readme4
+    count = 1000
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"devapi", 0, count, want_issuances=False)
+    pres[17, 0, 0] ^= 1
+    fields = torch.from_numpy(np.ascontiguousarray(pres.transpose(1, 0, 2))).cuda()
+    verdicts = torch.full((count,), 7, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        iss.verify_batch_device(kinds, count, fields.data_ptr(), verdicts.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    ov, _ = orc.verify_presentations(kinds, pres)
+    assert (verdicts.cpu().numpy() == ov).all() and ov[17] == 1 and ov.sum() == 1
+
+
+def test_full_size_batch_round_trip_properties(readme4):
+    """BASELINE config 2 size (65,536 x README-4) through size-independent properties: every honest presentation is
+    accepted, every item with a flipped bit is rejected, and nothing else changes (linearity of the corruption set)."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    orc, _, (sp, ip, sk) = readme4
+    base_n = 2048
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"full", 0, base_n, want_issuances=False)
+    reps = 65536 // base_n
+    big = np.tile(pres, (reps, 1, 1))
+    rng = np.random.default_rng(3)
+    bad = rng.choice(65536, 655, replace=False)
+    for i in bad:
+        w = rng.integers(0, 28)
+        big[i, w, rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+    iss = Issuer(sp, ip, sk, device=0, max_batch=65536)
+    v = iss.verify_batch(PresentationBatch.from_items(kinds, big))
+    expect = np.zeros(65536, np.uint8)
+    expect[bad] = 1
+    assert (v == expect).all()
+    sample = np.concatenate([bad[:64], rng.choice(65536, 64, replace=False)])
+    ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(big[sample]))
+    assert (v[sample] == ov).all()

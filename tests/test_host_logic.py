@@ -1,0 +1,122 @@
+"""CPU tests of everything around the kernels: the C ABI library loads and exports every symbol the header declares, and
+the shape compiler / marshaling / stage logic (compiled for the host by the test-only emulation harness, tests/hostemu)
+agree with the oracle on every golden shape.  No CUDA compute happens here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.common import GOLDEN_SHAPES, REQ, compare_with_oracle_trace, corrupt_batch, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_declared_symbols():
+    from aeonflux_b200 import build as B
+    so = B.build()
+    header = open(os.path.join(ROOT, "include", "aeonflux_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(afx_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(so)          # loads without a GPU: no CUDA call happens at load time
+    for name in declared:
+        assert hasattr(lib, name), "missing export " + name
+    from aeonflux_b200._binding import Binding
+    assert sorted(Binding.SYMBOLS) == declared
+    lib.afx_version.restype = ctypes.c_char_p
+    assert b"cuda sm_100a" in lib.afx_version()
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_has_no_cpu_fallback():
+    """The package never imports the oracle or the emulation harness, and refuses to run without the CUDA build."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "aeonflux_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".inc")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "hostemu.so" not in src, f
+    import aeonflux_b200._lib as lib
+    saved, lib._binding, lib.SO_PATH = (lib._binding, lib.SO_PATH), None, "/nonexistent/libaeonflux_b200.so"
+    try:
+        with pytest.raises(ImportError):
+            lib.load()
+    finally:
+        lib._binding, lib.SO_PATH = saved
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """The host-emulation build of the same C ABI (tests only)."""
+    d = os.path.join(ROOT, "tests", "hostemu")
+    so, src = os.path.join(d, "libafx_hostemu.so"), os.path.join(d, "hostemu.cpp")
+    csrc = os.path.join(ROOT, "aeonflux_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc) if not f.endswith(".so"))
+    if not os.path.exists(so) or os.path.getmtime(so) < max(newest, os.path.getmtime(src)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-x", "c++", "-o", so, src])
+    from aeonflux_b200._binding import Binding
+    return Binding(ctypes.CDLL(so))
+
+
+@pytest.mark.parametrize("name", GOLDEN_SHAPES)
+def test_stage_logic_matches_oracle_on_golden_shapes(emu, coracle, name):
+    from aeonflux_b200 import Issuer, PresentationBatch
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    orc = coracle.Issuer(sp, ip, sk)
+    rk = bytes(REQ[k] for k in g["request"])
+    kinds, pres, issu = orc.synth(rk, g["hide"], g["config"].encode(), 0, 5)
+    e = g["items"][0]
+    assert pres[0].tobytes().hex() == "".join(e["words"])
+    pres[1, 1, 3] ^= 0x10
+    pres[3, 0, 0] ^= 1
+    iss = Issuer(sp, ip, sk, max_batch=3, _binding=emu)      # max_batch < count exercises chunking
+    v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    compare_with_oracle_trace(v, dbg, ov, tr)
+    assert dbg["Z"][0].tobytes().hex() == e["Z"]
+    assert dbg["commitments"][:len(e["commitments"]), 0].tobytes().hex() == "".join(e["commitments"])   # filled as far as the reference gets
+    assert dbg["challenges"][:len(e["challenges"]), 0].tobytes().hex() == "".join(e["challenges"])
+    ik = bytes(e["issuance_kinds"])
+    issu[2, len(ik) + 1, 5] ^= 2
+    vi, dbgi = iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu), debug=True)
+    ovi, _, tri = orc.verify_issuances(ik, issu, trace=True)
+    compare_with_oracle_trace(vi, dbgi, ovi, tri)
+    assert dbgi["commitments"][:, 0].tobytes().hex() == "".join(e["issuance_commitments"])
+    user = Issuer(sp, ip, None, max_batch=8, _binding=emu)     # user-side context: no secret key
+    assert (user.verify_issuance_batch(PresentationBatch.from_items(ik, issu)) == ovi).all()
+
+
+def test_corruption_classes_and_edges(emu, coracle):
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from aeonflux_b200._binding import AfxError
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"edges", 0, 40, want_issuances=False)
+    rng = np.random.default_rng(7)
+    pts = pres[:, 5:8].reshape(-1, 32).copy()
+    idx = corrupt_batch(pres, kinds, rng, 0.5, pts)
+    iss = Issuer(sp, ip, sk, max_batch=64, _binding=emu)
+    v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    compare_with_oracle_trace(v, dbg, ov, tr)
+    assert ov[idx].all() and not np.delete(ov, idx).any()
+    # empty batch
+    assert len(iss.verify_batch(PresentationBatch(kinds, np.zeros((28, 0, 32), np.uint8)))) == 0
+    # wrong field count, wrong attribute count, missing secret
+    with pytest.raises(AfxError):
+        iss.verify_batch(PresentationBatch(kinds, np.zeros((27, 2, 32), np.uint8)))
+    with pytest.raises(AfxError):
+        iss.verify_batch(PresentationBatch(bytes([0, 0, 0]), np.zeros((12, 1, 32), np.uint8)))
+    user = Issuer(sp, ip, None, max_batch=4, _binding=emu)
+    with pytest.raises(AfxError):
+        user.verify_batch(PresentationBatch.from_items(kinds, pres[:2]))
+    # issuer material that does not decode
+    bad = bytearray(sp); bad[4 + 32] ^= 1
+    with pytest.raises(AfxError):
+        Issuer(bytes(bad), ip, sk, _binding=emu)
+    with pytest.raises(AfxError):
+        Issuer(sp[:-1], ip, sk, _binding=emu)
