@@ -26,7 +26,7 @@ class AfxError(RuntimeError):
 class Binding:
     SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
                "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
-               "afx_launch_count", "afx_ctx_device", "afx_strerror", "afx_version"]
+               "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -46,6 +46,10 @@ class Binding:
         L.afx_verify_presentations_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp]
         L.afx_launch_count.restype = ctypes.c_uint64
         L.afx_launch_count.argtypes = [vp]
+        L.afx_set_stage_timing.restype = None
+        L.afx_set_stage_timing.argtypes = [vp, ctypes.c_int]
+        L.afx_get_stage_times.restype = ctypes.c_int
+        L.afx_get_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
         L.afx_ctx_device.restype = ctypes.c_int
         L.afx_ctx_device.argtypes = [vp]
         L.afx_strerror.restype = ctypes.c_char_p

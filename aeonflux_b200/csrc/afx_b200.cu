@@ -107,6 +107,12 @@ static int be_check_launch() {
     if (e != cudaSuccess) { std::fprintf(stderr, "aeonflux_b200: CUDA launch failed: %s\n", cudaGetErrorString(e)); return -3; }
     return 0;
 }
+typedef cudaEvent_t be_event;
+static void be_event_create(be_event* e) { cudaEventCreate(e); }
+static void be_event_destroy(be_event e) { cudaEventDestroy(e); }
+static void be_event_record(be_event e, be_stream s) { cudaEventRecord(e, s); }
+static int be_event_sync(be_event e) { return cudaEventSynchronize(e) != cudaSuccess; }
+static float be_event_elapsed(be_event a, be_event b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 static dim3 grid_for(u32 count, u32 tpb, u32 y) { return dim3((count + tpb - 1) / tpb, y, 1); }
 
 static void be_launch_scalar_check(const Workspace& ws, const u16* d_fields, u32 nf, be_stream s) {

@@ -92,6 +92,17 @@ class Issuer:
     def launch_count(self):
         return int(self._b.L.afx_launch_count(self._h))
 
+    STAGES = ("scalar_check", "points", "amac", "msm", "transcript", "verdict")
+
+    def set_stage_timing(self, on: bool):
+        self._b.L.afx_set_stage_timing(self._h, 1 if on else 0)
+
+    def stage_times_ms(self):
+        """Device time of each stage of the most recent run (CUDA events on the launching stream)."""
+        ms = (ctypes.c_float * 6)()
+        self._b.check(self._b.L.afx_get_stage_times(self._h, ms, 6))
+        return dict(zip(self.STAGES, [float(x) for x in ms]))
+
     def _run(self, fn, batch, ncommit, nproofs, debug):
         count = batch.count
         ptrs, keep = B._as_fields(batch.fields)

@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- presentations verified/sec (Issuer::verify, 4 attributes) on N B200s, with the integer-pipe roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one pass of the hot path (afx_verify_presentations) over one batch of B = 65,536 README-4 presentations per GPU
+(BASELINE.json configs[1]).  `value` is timed with the batch resident in HBM (CUDA events on the launching stream, L2
+flushed between steps); `e2e` is the same call through the host-buffer C ABI with the H2D copy of the 896-byte items and
+the D2H copy of the verdicts inside the timed region.  Ranks are independent (weak scaling: every rank verifies its own
+65,536-item slice with a replicated issuer context; only the accept/reject counts are gathered).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KINDS_README4 = bytes([1, 0, 2, 3])   # [SecretScalar, PublicScalar, PublicPoint, SecretPoint]  (README.md:44-117, attrs 0 and 3 hidden)
+WORDS = 28
+
+# ---- algorithmic work model: limb-products per field op, 1 limb-product = 2 IMAD issue slots (IMAD.WIDE is half rate,
+# measured: profiles/r01_microbench_imad.json) ----------------------------------------------------------------------------------
+S_LP, M_LP = 44, 72
+DBL, ADD, MADD = 4 * S_LP + 4 * M_LP, 8 * M_LP, 7 * M_LP
+DECOMPRESS, COMPRESS = 258 * S_LP + 24 * M_LP, 256 * S_LP + 30 * M_LP
+TABLE = DBL + 7 * ADD
+
+
+def work_model(kinds):
+    """Algorithmic limb-products per item and per stage for a presentation shape (minimal schedule of SURVEY 8d)."""
+    n = len(kinds)
+    r_s, h_s = sum(k == 0 for k in kinds), sum(k == 1 for k in kinds)
+    r_p, h_p = sum(k == 2 for k in kinds), sum(k == 3 for k in kinds)
+    n_dec = 3 + n + r_p + 7 * h_p
+    n_msm = 2 + h_s + r_s + r_p + 5 * h_p
+    var_terms = 1 + 2 + h_s + r_s + r_p + h_p * (1 + 2 + 2 + 3 + 1)
+    con_terms = 1 + 2 + 2 * h_s + r_s + r_p + h_p * (3 + 1 + 0 + 1 + 2)
+    points = n_dec * DECOMPRESS + (var_terms - 1) * TABLE + 2 * h_p * COMPRESS
+    amac = 252 * DBL + (2 + n) * (7 + 64) * ADD + r_s * 64 * MADD + (r_s + r_p + 2) * ADD + COMPRESS + TABLE
+    msm = n_msm * 253 * DBL + var_terms * (253 / 6) * ADD + con_terms * (253 / 9) * MADD + n_msm * COMPRESS
+    total = points + amac + msm
+    return {"points": points, "amac": amac, "msm": msm, "total": total}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.rows.append(line) for line in self.proc.stdout], daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_fixture(batch):
+    pres = np.fromfile(os.path.join(ROOT, "bench_data", "readme4_1024.bin"), np.uint8).reshape(-1, WORDS, 32)
+    blob = open(os.path.join(ROOT, "bench_data", "issuer4.bin"), "rb").read()
+    sp, ip, sk = blob[:548], blob[548:612], blob[612:]
+    reps = (batch + len(pres) - 1) // len(pres)
+    items = np.tile(pres, (reps, 1, 1))[:batch]
+    return sp, ip, sk, items
+
+
+def cpu_leg(sp, ip, sk, items, sample, threads):
+    """The restated reference CPU path (oracle/c, reference schedule) on `sample` items with `threads` host threads."""
+    from oracle import coracle as C
+    C.build()
+    orc = C.Issuer(sp, ip, sk)
+    sub = np.ascontiguousarray(items[:sample])
+    t0 = time.perf_counter()
+    verdicts, _ = orc.verify_presentations(KINDS_README4, sub, threads=threads)
+    wall = time.perf_counter() - t0
+    return verdicts, sample / wall, wall
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU schedule of Issuer::verify on the host cores.  The Rust crate cannot be
+    built in this image (no rustc/cargo, un-vendored deps), so this is the C restatement of its schedule (oracle/c)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sp, ip, sk, items = load_fixture(args.batch)
+    sample = max(cores * 64, 2048)
+    for _ in range(args.warmup):
+        cpu_leg(sp, ip, sk, items, min(sample, cores * 16), cores)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, rate, wall = cpu_leg(sp, ip, sk, items, sample, cores)
+        assert not v.any()
+        t_total += wall; n_total += sample
+    value = n_total / t_total
+    line = {"impl": "reference", "metric": "presentations_verified_per_sec", "value": value, "unit": "presentations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 (5x51-bit limbs, like dalek u64_backend)", "data": "synthetic",
+            "config": {"workload": "Issuer::verify, README-4 presentations [SS,PS,PP,SP], %d-item sample per step of the 65,536-item batch" % sample},
+            "cpu_baseline": {"value": value, "unit": "presentations/s", "cores": cores, "kind": "port",
+                             "sample": "%d items/step x %d steps, C restatement of the reference schedule (not the Rust binary)" % (sample, args.steps)},
+            "e2e": {"value": value, "unit": "presentations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from aeonflux_b200 import Issuer, PresentationBatch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    sp, ip, sk, items = load_fixture(B)
+    if world > 1:   # each rank takes its own slice of the global stream: rotate so the ranks do not hold identical bytes
+        items = np.roll(items, rank * 131, axis=0)
+    issuer = Issuer(sp, ip, sk, device=local, max_batch=B)
+    # host staging in pinned memory (the e2e leg copies from here); SoA [field][item][32]
+    host = torch.empty((WORDS, B, 32), dtype=torch.uint8).pin_memory()
+    host.numpy()[:] = items.transpose(1, 0, 2)
+    fields_dev = host.cuda(non_blocking=False)
+    verdicts_dev = torch.empty(B, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    kinds = KINDS_README4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        issuer.verify_batch_device(kinds, B, fields_dev.data_ptr(), verdicts_dev.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        return e0, e1
+
+    # ---- kernel-only: inputs resident in HBM --------------------------------------------------------------------
+    issuer.set_stage_timing(True)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    launches0 = issuer.launch_count
+    stage_sum = {k: 0.0 for k in Issuer.STAGES}
+    with ClockSampler(local) as clocks:
+        evs = []
+        for _ in range(args.steps):
+            evs.append(step_device())
+            torch.cuda.synchronize()
+            for k, v in issuer.stage_times_ms().items():
+                stage_sum[k] += v
+        barrier()
+    launches = issuer.launch_count - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    assert int(verdicts_dev.sum().item()) == 0, "honest presentations were rejected"
+    issuer.set_stage_timing(False)
+
+    # ---- end to end: host buffers through the C ABI, H2D + kernels + D2H per step --------------------------------------
+    batch = PresentationBatch(kinds, host.numpy())
+    for _ in range(2):
+        issuer.verify_batch(batch)
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        v = issuer.verify_batch(batch)
+        e2e_s += time.perf_counter() - t0
+        assert not v.any()
+    barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_items = world * B * args.steps
+    value = total_items / (dev_ms_max * 1e-3)
+    e2e_value = total_items / (e2e_ms_max * 1e-3)
+    wm = work_model(kinds)
+    clk = clocks.summary()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    sm_max = clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    imad_peak = 148 * 64 * sm_max * 1e6                       # IMAD issue slots/s at max clock (measured 18.52e12 by tools/microbench)
+    msm_ms = stage_sum["msm"] / args.steps
+    msm_imad = 2 * wm["msm"] * B                              # algorithmic IMAD slots per launch group of the dominant kernel (k_msm)
+    achieved = msm_imad / (msm_ms * 1e-3)
+    hbm_bytes = B * (WORDS * 32 + 1)
+    roofline = {"bound": "imad", "kernel": "k_msm", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": achieved / imad_peak,
+                "traffic": None, "peak_source": "148 SMs x 64 IMAD/clk x sm_max_mhz; tools/microbench measured 18.52 T IMAD/s and 9.12 T IMAD.WIDE/s (profiles/r01_microbench_imad.json)",
+                "algorithmic_imad_per_item": {k: 2 * v for k, v in wm.items()},
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_sum.items()},
+                "pipeline_frac_of_imad_peak": (B * args.steps * 2 * wm["total"] / (dev_ms * 1e-3)) / imad_peak,
+                "pipeline_frac_at_observed_clock": ((B * args.steps * 2 * wm["total"] / (dev_ms * 1e-3)) / (148 * 64 * clk["sm_mhz"] * 1e6)) if clk.get("sm_mhz") else None,
+                "hbm": {"algorithmic_GBps": hbm_bytes * args.steps / (dev_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs", 6650.0),
+                        "note": "non-binding: 897 B of input/output per presentation"}}
+    line = {"metric": "presentations_verified_per_sec", "value": value, "unit": "presentations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE carry chains)",
+            "data": "synthetic", "config": {"workload": "batch Issuer::verify of 65,536 README-4 presentations [SS,PS,PP,SP] per GPU (BASELINE configs[1])",
+                                            "batch_per_gpu": B, "kinds": list(kinds), "bytes_per_item": WORDS * 32,
+                                            "l2": "256 MiB flush write between timed steps; 1.2 GB workspace per step exceeds L2",
+                                            "input": "1,024 distinct presentations tiled to the batch (bench_data/make_fixture.py)"},
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "presentations/s", "h2d_bytes_per_step": B * WORDS * 32, "d2h_bytes_per_step": B, "ms_per_step": e2e_ms_max / args.steps},
+            "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = max(cores * 128, 4096)
+        cv, rate, wall = cpu_leg(sp, ip, sk, items, sample, cores)
+        gv = issuer.verify_batch(PresentationBatch.from_items(kinds, items[:sample]))
+        assert (cv == gv).all(), "GPU verdicts differ from the CPU restatement"
+        _, rate1, _ = cpu_leg(sp, ip, sk, items, max(sample // cores, 256), 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "presentations/s", "cores": cores, "kind": "port", "single_core_value": rate1,
+                                "sample": "%d items of the same batch, %.1f s, C restatement of the reference CPU schedule (oracle/c), verdicts cross-checked with the GPU" % (sample, wall)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,22 @@
+"""Writes bench_data/readme4_1024.bin: 1,024 distinct honest README-4 presentations (kinds [SS,PS,PP,SP], 28 words of 32 B
+each, item-major) plus the issuer they verify under (bench_data/issuer4.bin = sysparams || C_W||I || secret key), generated
+with the oracle's reference-schedule prover from the fixed SHAKE-256 seeds of SURVEY 8d (config "bench-readme4").
+bench.py tiles these to the 65,536-item batch of BASELINE config 2: every item is independent and every stage's control flow
+is data-independent, so tiling changes neither the work nor the memory traffic (each item still owns its own workspace rows).
+Run from the repo root:  python bench_data/make_fixture.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import coracle as C  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sp, ip, sk = C.make_issuer(4)
+iss = C.Issuer(sp, ip, sk)
+kinds, pres, _ = iss.synth(b"SSPE", [0, 3], b"bench-readme4", 0, 1024, want_issuances=False)
+assert list(kinds) == [1, 0, 2, 3]
+v, _ = iss.verify_presentations(kinds, pres)
+assert not v.any()
+pres.tofile(os.path.join(HERE, "readme4_1024.bin"))
+open(os.path.join(HERE, "issuer4.bin"), "wb").write(sp + ip + sk)
+print("wrote", pres.shape, len(sp), len(ip), len(sk))

@@ -100,6 +100,13 @@ int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t*
 /* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */
 uint64_t afx_launch_count(const afx_ctx* ctx);
 
+/* Per-stage device timing for the roofline report.  When enabled, every pipeline run records CUDA events between its
+ * stages on the launching stream; afx_get_stage_times waits for the last run and returns the AFX_NUM_STAGES durations in
+ * milliseconds, in order: scalar checks, points (decompress + tables), aMAC ladder, constraint MSMs, transcripts, verdict. */
+#define AFX_NUM_STAGES 6
+void afx_set_stage_timing(afx_ctx* ctx, int on);
+int afx_get_stage_times(afx_ctx* ctx, float* ms, int n);
+
 /* Device time of the most recent *_device / host call's kernel sequence is measured by the caller with events on the
  * stream it passed; this returns the ordinal of the CUDA device the context lives on. */
 int afx_ctx_device(const afx_ctx* ctx);

@@ -22,6 +22,12 @@ static int be_d2h(void* h, const void* d, size_t n, be_stream) { std::memcpy(h, 
 static int be_memset(void* d, int v, size_t n, be_stream) { std::memset(d, v, n); return 0; }
 static int be_sync(be_stream) { return 0; }
 static int be_check_launch() { return 0; }
+typedef int be_event;
+static void be_event_create(be_event*) {}
+static void be_event_destroy(be_event) {}
+static void be_event_record(be_event, be_stream) {}
+static int be_event_sync(be_event) { return 0; }
+static float be_event_elapsed(be_event, be_event) { return 0.f; }
 
 static void be_launch_scalar_check(const Workspace& ws, const u16* f, u32 nf, be_stream) {
     for (u32 k = 0; k < nf; k++) for (u32 i = 0; i < ws.count; i++) scalar_check_job(ws, f[k], i);
