@@ -14,6 +14,7 @@
 namespace afx {
 
 constexpr int TPB = 128;            // threads per CTA for the ladder kernels (4 warps, one per SMSP)
+constexpr int TPB_MSM = 512;        // one lockstep CTA per SM for the constraint ladders (16 warps share the I-cache)
 constexpr int MSM_STAGE_TABLES = 3; // constant-base tables staged in shared memory per CTA (12 KB each)
 
 __global__ void __launch_bounds__(256) k_scalar_check(Workspace ws, const u16* fields) {
@@ -21,22 +22,22 @@ __global__ void __launch_bounds__(256) k_scalar_check(Workspace ws, const u16* f
     if (item < ws.count) scalar_check_job(ws, fields[blockIdx.y], item);
 }
 
-__global__ void __launch_bounds__(TPB) k_points(Workspace ws, const PointJob* jobs) {
+__global__ void __launch_bounds__(TPB, 4) k_points(Workspace ws, const PointJob* jobs) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < ws.count) points_job(ws, jobs[blockIdx.y], item);
 }
 
-__global__ void __launch_bounds__(TPB) k_amac(Workspace ws, const AmacDesc* d) {
+__global__ void __launch_bounds__(TPB, 4) k_amac(Workspace ws, const AmacDesc* d) {
     extern __shared__ u32 smem[];
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < ws.count) amac_job(ws, *d, item, smem + threadIdx.x, blockDim.x);
 }
 
-__global__ void __launch_bounds__(TPB) k_msm(Workspace ws, const MsmDesc* msms, const u32* group_idx, u32 scratch_terms) {
+__global__ void __launch_bounds__(TPB_MSM, 1) k_msm(Workspace ws, const MsmDesc* msms, const u32* group_idx, u32 scratch_terms) {
     extern __shared__ __align__(16) u32 smem[];
     const MsmDesc& d = msms[group_idx[blockIdx.y]];
-    u32* scratch = smem;                                          // [scratch_terms*8][TPB]
-    u32* staged = smem + (size_t)scratch_terms * 8 * TPB;         // [<=MSM_STAGE_TABLES][128][24]
+    u32* scratch = smem;                                          // [scratch_terms*8][TPB_MSM]
+    u32* staged = smem + (size_t)scratch_terms * 8 * blockDim.x;  // [<=MSM_STAGE_TABLES][128][24]
     u32 nstage = d.ncon < MSM_STAGE_TABLES ? d.ncon : MSM_STAGE_TABLES;
     for (u32 k = 0; k < nstage; k++) {
         const uint4* src = reinterpret_cast<const uint4*>(ws.ctabs + (size_t)d.con[k].ctab * CTAB_ENTRIES * 24);
@@ -45,9 +46,10 @@ __global__ void __launch_bounds__(TPB) k_msm(Workspace ws, const MsmDesc* msms, 
     }
     __syncthreads();
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= ws.count) return;
+    bool active = item < ws.count;
+    if (!active) item = ws.count - 1;                              // keep every thread in the barriers of the ladder
     CtabResolver ctab_of{staged, ws.ctabs, &d, nstage};
-    msm_job(ws, d, item, scratch + threadIdx.x, blockDim.x, ctab_of);
+    msm_job(ws, d, item, scratch + threadIdx.x, blockDim.x, ctab_of, active);
 }
 
 __global__ void __launch_bounds__(TPB) k_transcript(Workspace ws, const TxDesc* txs) {
@@ -129,10 +131,16 @@ static void be_launch_amac(const Workspace& ws, const AmacDesc* d, u32 nps, be_s
 }
 static void be_launch_msm(const Workspace& ws, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 max_terms, u32 max_con, be_stream s) {
     u32 nstage = max_con < (u32)MSM_STAGE_TABLES ? max_con : (u32)MSM_STAGE_TABLES;
-    size_t smem = (size_t)max_terms * 8 * TPB * 4 + (size_t)nstage * CTAB_ENTRIES * 96;
+    // largest CTA (<= TPB_MSM threads) whose digit scratch + staged tables fit in shared memory
+    u32 tpb = TPB_MSM;
+    size_t smem = 0;
+    for (;; tpb /= 2) {
+        smem = (size_t)max_terms * 8 * tpb * 4 + (size_t)nstage * CTAB_ENTRIES * 96;
+        if (smem <= 200 * 1024 || tpb <= 32) break;
+    }
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
-    k_msm<<<grid_for(ws.count, TPB, nidx), TPB, smem, s>>>(ws, d_msms, d_idx, max_terms);
+    k_msm<<<grid_for(ws.count, tpb, nidx), tpb, smem, s>>>(ws, d_msms, d_idx, max_terms);
 }
 static void be_launch_transcript(const Workspace& ws, const TxDesc* d_txs, u32 ntx, be_stream s) {
     k_transcript<<<grid_for(ws.count, TPB, ntx), TPB, 0, s>>>(ws, d_txs);

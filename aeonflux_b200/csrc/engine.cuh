@@ -107,6 +107,14 @@ AFX_HD void store8(u32* dst, const u32* src) {
     for (int i = 0; i < 8; i++) dst[i] = src[i];
 #endif
 }
+// Pull a 1 KiB ladder table towards L2 ahead of the constant-address scan that will read all of it.
+AFX_HD void prefetch_table(const u32* table) {
+#if defined(__CUDA_ARCH__)
+    for (int e = 0; e < 8; e++) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + 32 * e));
+#else
+    (void)table;
+#endif
+}
 AFX_HD fe load_fe(const u32* src) { fe r; load8(r.v, src); return r; }
 AFX_HD void store_fe(u32* dst, const fe& a) { store8(dst, a.v); }
 AFX_HD ge load_ge(const u32* src) { ge p; p.X = load_fe(src); p.Y = load_fe(src + 8); p.Z = load_fe(src + 16); p.T = load_fe(src + 24); return p; }
@@ -173,24 +181,43 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
 AFX_HD pniels pniels_scan_select(const u32* table, int digit) {
     u32 neg = (u32)digit >> 31;
     u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
-    pniels r = pniels_identity();
+#ifdef AFX_EXPERIMENT_DIRECT
+    { pniels r = pniels_identity(); if (mag) r = load_pniels(table + 32 * (mag - 1)); return pniels_cneg(r, neg); }
+#endif
+    // every entry is read (128 contiguous bytes per load group) and OR-ed in under a mask
+    u32 out[32];
+    for (int i = 0; i < 32; i++) out[i] = 0;
     for (u32 e = 1; e <= 8; e++) {
-        pniels c = load_pniels(table + 32 * (e - 1));
-        u32 take = (e == mag);
-        r.YpX = fe_select(r.YpX, c.YpX, take); r.YmX = fe_select(r.YmX, c.YmX, take);
-        r.Z = fe_select(r.Z, c.Z, take); r.T2d = fe_select(r.T2d, c.T2d, take);
+        u32 m = 0u - (u32)(e == mag);
+        for (int q = 0; q < 4; q++) {
+            u32 w[8]; load8(w, table + 32 * (e - 1) + 8 * q);
+            for (int i = 0; i < 8; i++) out[8 * q + i] |= w[i] & m;
+        }
     }
+    u32 z = (mag == 0);   // digit 0 -> the identity (1, 1, 1, 0)
+    out[0] |= z; out[8] |= z; out[16] |= z;
+    pniels r;
+    for (int i = 0; i < 8; i++) { r.YpX.v[i] = out[i]; r.YmX.v[i] = out[8 + i]; r.Z.v[i] = out[16 + i]; r.T2d.v[i] = out[24 + i]; }
     return pniels_cneg(r, neg);
 }
 AFX_HD aniels aniels_scan_select8(const u32* ctab, int digit) {
     u32 neg = (u32)digit >> 31;
     u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
-    aniels r = aniels_identity();
-    for (u32 e = 1; e <= 8; e++) {
-        aniels c = load_aniels(ctab + 24 * (e - 1));
-        u32 take = (e == mag);
-        r.ypx = fe_select(r.ypx, c.ypx, take); r.ymx = fe_select(r.ymx, c.ymx, take); r.xy2d = fe_select(r.xy2d, c.xy2d, take);
+    u32 out[24];
+    for (int comp = 0; comp < 3; comp++) {
+        u32 acc[8];
+        for (int i = 0; i < 8; i++) acc[i] = 0;
+        for (u32 e = 1; e <= 8; e++) {
+            u32 w[8]; load8(w, ctab + 24 * (e - 1) + 8 * comp);
+            u32 m = 0u - (u32)(e == mag);
+            for (int i = 0; i < 8; i++) acc[i] |= w[i] & m;
+        }
+        for (int i = 0; i < 8; i++) out[8 * comp + i] = acc[i];
     }
+    u32 z = (mag == 0);
+    out[0] |= z; out[8] |= z;
+    aniels r;
+    for (int i = 0; i < 8; i++) { r.ypx.v[i] = out[i]; r.ymx.v[i] = out[8 + i]; r.xy2d.v[i] = out[16 + i]; }
     return aniels_cneg(r, neg);
 }
 
@@ -210,6 +237,7 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
         for (u32 k = 0; k < d.nvar; k++) {
             int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
             pniels e = pniels_scan_select(table_ptr(ws, d.var[k].table_slot, item), dig);
+            prefetch_table(table_ptr(ws, d.var[k + 1 < d.nvar ? k + 1 : 0].table_slot, item));   // next lookup, hidden behind this add
             acc = ge_add_pn(acc, e, true);
         }
         for (u32 k = 0; k < d.nps; k++) {
@@ -241,7 +269,7 @@ struct CtabResolver {
 // scratch: (nvar + ncon) * 8 words per item of recoded scalars.  ctab_of(k) returns the table base of constant term k
 // (shared-memory staged on the device, global otherwise).
 template <typename CtabOf>
-AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, CtabOf ctab_of) {
+AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, CtabOf ctab_of, bool active = true) {
     for (u32 k = 0; k < d.nvar; k++) {
         u32 rec[8];
         sc_recode16(rec, eval_scalar(ws, d.var[k].s, item));
@@ -254,6 +282,9 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
     }
     ge acc = ge_identity();
     for (int i = 63; i >= 0; i--) {
+#if defined(__CUDA_ARCH__)
+        AFX_STEP_SYNC();
+#endif
         if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
         for (u32 k = 0; k < d.nvar; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
@@ -280,7 +311,7 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
     }
     u32 w[8];
     ge_compress(w, acc);
-    store8(commit_ptr(ws, d.out_slot, item), w);
+    if (active) store8(commit_ptr(ws, d.out_slot, item), w);
 }
 
 // ---- stage: transcript -------------------------------------------------------------------------------------------

@@ -21,9 +21,15 @@
 // Point-level operations are real subroutines on the device (ptxas keeps their by-value struct arguments in registers):
 // this keeps each kernel's code to tens of KB instead of megabytes of inlined multiplies.
 #define AFX_NI __host__ __device__ __noinline__
+// Keeps the warps of a CTA within one ladder step of each other so that they share instruction-cache lines.
+#define AFX_STEP_SYNC() __syncthreads()
 #else
+#define AFX_STEP_SYNC() do { } while (0)
 #define AFX_HD inline
 #define AFX_NI inline
+#ifndef AFX_STEP_SYNC
+#define AFX_STEP_SYNC() do { } while (0)
+#endif
 #endif
 
 namespace afx {
