@@ -52,6 +52,26 @@ __global__ void __launch_bounds__(TPB_MSM, 1) k_msm(Workspace ws, const MsmDesc*
     msm_job(ws, d, item, scratch + threadIdx.x, blockDim.x, ctab_of, active);
 }
 
+// Issuer::issue: the same per-(item, job) ladders with every lookup constant-address (all scalars are secrets)
+__global__ void __launch_bounds__(TPB_MSM, 1) k_msm_ct(Workspace ws, const MsmDesc* msms, const u32* group_idx) {
+    extern __shared__ __align__(16) u32 smem[];
+    const MsmDesc& d = msms[group_idx[blockIdx.y]];
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = item < ws.count;
+    if (!active) item = ws.count - 1;
+    msm_ct_job(ws, d, item, smem + threadIdx.x, blockDim.x, active);
+}
+
+__global__ void __launch_bounds__(256) k_derive(Workspace ws, const WideDesc* d) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.count) derive_job(ws, d[blockIdx.y], blockIdx.y, item);
+}
+
+__global__ void __launch_bounds__(256) k_issue_out(Workspace ws, const IssueOutDesc* d, u32* out) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.count) issue_out_job(ws, *d, blockIdx.y, item, out);
+}
+
 __global__ void __launch_bounds__(TPB) k_transcript(Workspace ws, const TxDesc* txs) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < ws.count) transcript_job(ws, txs[blockIdx.y], item);
@@ -141,6 +161,23 @@ static void be_launch_msm(const Workspace& ws, const MsmDesc* d_msms, const u32*
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
     k_msm<<<grid_for(ws.count, tpb, nidx), tpb, smem, s>>>(ws, d_msms, d_idx, max_terms);
+}
+static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 max_terms, be_stream s) {
+    u32 tpb = TPB_MSM;
+    size_t smem = 0;
+    for (;; tpb /= 2) {
+        smem = (size_t)max_terms * 8 * tpb * 4;
+        if (smem <= 200 * 1024 || tpb <= 32) break;
+    }
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_msm_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
+    k_msm_ct<<<grid_for(ws.count, tpb, nidx), tpb, smem, s>>>(ws, d_msms, d_idx);
+}
+static void be_launch_derive(const Workspace& ws, const WideDesc* d, u32 nd, be_stream s) {
+    k_derive<<<grid_for(ws.count, 256, nd), 256, 0, s>>>(ws, d);
+}
+static void be_launch_issue_out(const Workspace& ws, const IssueOutDesc* d, u32 nwords, u32* out, be_stream s) {
+    k_issue_out<<<grid_for(ws.count, 256, nwords), 256, 0, s>>>(ws, d, out);
 }
 static void be_launch_transcript(const Workspace& ws, const TxDesc* d_txs, u32 ntx, be_stream s) {
     k_transcript<<<grid_for(ws.count, TPB, ntx), TPB, 0, s>>>(ws, d_txs);

@@ -28,18 +28,22 @@ constexpr int MAX_CONST_TERMS = MAX_ATTRS + 8;
 constexpr int CTAB_ENTRIES = 128;  // radix-256 signed digits: multiples 1..128 of a constant base
 
 // ---- scalar sources ---------------------------------------------------------------------------
-enum : u32 { SC_FIELD = 0, SC_MUL = 1, SC_MULADD = 2 };  // F[f0] | F[f0]*F[f1] | F[f0] + F[f1]*F[f2]
+enum : u32 { SC_FIELD = 0, SC_MUL = 1, SC_MULADD = 2 };  // R[f0] | R[f0]*R[f1] | R[f0] + R[f1]*R[f2]
+// A scalar reference R[f] names an input field (f < 0x4000), an issuer-secret row (SREF_SECRET | row: x_0, x_1, y_i, w, w')
+// or a per-item derived scalar (SREF_DERIVED | slot: the wide-reduced t and blindings of Issuer::issue).
+enum : u32 { SREF_SECRET = 0x4000, SREF_DERIVED = 0x8000, SREF_MASK = 0x3fff };
 struct ScalarSrc { u16 op, f0, f1, f2; };
 
 struct VarTerm { u16 table_slot; u16 neg; ScalarSrc s; };
 struct ConstTerm { u16 ctab; u16 neg; ScalarSrc s; };
+enum : u32 { MSM_ADD_W = 1 };   // flags: add the issuer's W after the ladder (Amac::compute_V, amacs.rs:267)
 struct MsmDesc {
-    u16 nvar, ncon, out_slot, pad;
+    u16 nvar, ncon, out_slot, flags;
     VarTerm var[MAX_VAR_TERMS];
     ConstTerm con[MAX_CONST_TERMS];
 };
 
-enum : u32 { PJ_COPY = 0, PJ_ADD = 1, PJ_SUB = 2 };
+enum : u32 { PJ_COPY = 0, PJ_ADD = 1, PJ_SUB = 2, PJ_UNIFORM = 3 };  // PJ_UNIFORM: from_uniform_bytes(field_a || field_b)
 struct PointJob {
     int16_t field_a, field_b;      // input point fields (field_b = -1 for PJ_COPY)
     u16 op, pad;
@@ -66,6 +70,14 @@ struct TxDesc {
     u64 midstate[25];
 };
 
+// Issuer::issue epilogue (issuer.rs:111-124 / zkp prove_compact): output words t, U, V, challenge, responses[n+5]
+struct WideDesc { u16 lo, hi; };                       // derived scalar k = (F[lo] || F[hi]) mod l  (Scalar::random's wide reduction)
+struct IssueOutDesc {
+    u16 nresp, comp_U, commit_V, der_t;
+    u16 resp_sec[MAX_ATTRS + 5];                       // secret row of witness k, 0xffff = the constant scalar "1"
+    u16 resp_blind[MAX_ATTRS + 5];                     // derived slot of blinding k
+};
+
 // ---- workspace ------------------------------------------------------------------------------------
 // All arrays are slot-major then item-major; an item's 32-byte word is 8 consecutive u32 (two 128-bit loads).
 struct Workspace {
@@ -77,6 +89,7 @@ struct Workspace {
     u32* commit;         // [n_msm][count][8]
     u32* chal;           // [n_proofs][count][8]  recomputed challenges
     u32* status;         // [count]   0 = ok so far
+    u32* derived;        // [n_derived][count][8]  per-item derived scalars (Issuer::issue only)
     // per-issuer constants
     const u32* ctabs;    // [n_ctab][128][24]  affine Niels multiples 1..128
     const u32* secdig;   // [n_secret][8]      radix-16 recoded secret scalars (packed nibbles)
@@ -140,12 +153,18 @@ AFX_HD void status_or(const Workspace& ws, u32 item, u32 bits) {
 #endif
 }
 
+AFX_HD const u32* scalar_ref_ptr(const Workspace& ws, u32 ref, u32 item) {
+    if (ref & SREF_DERIVED) return ws.derived + ((size_t)(ref & SREF_MASK) * ws.count + item) * 8;
+    if (ref & SREF_SECRET) return ws.secsc + 8 * (ref & SREF_MASK);
+    return field_ptr(ws, ref, item);
+}
+AFX_HD sc load_sc(const u32* p) { u32 w[8]; load8(w, p); return sc_from_words(w); }
 AFX_HD sc eval_scalar(const Workspace& ws, const ScalarSrc& s, u32 item) {
-    sc a = sc_from_words(field_ptr(ws, s.f0, item));
+    sc a = load_sc(scalar_ref_ptr(ws, s.f0, item));
     if (s.op == SC_FIELD) return a;
-    sc b = sc_from_words(field_ptr(ws, s.f1, item));
+    sc b = load_sc(scalar_ref_ptr(ws, s.f1, item));
     if (s.op == SC_MUL) return sc_mul(a, b);
-    sc c = sc_from_words(field_ptr(ws, s.f2, item));
+    sc c = load_sc(scalar_ref_ptr(ws, s.f2, item));
     return sc_muladd(b, c, a);
 }
 
@@ -159,9 +178,16 @@ AFX_HD void scalar_check_job(const Workspace& ws, u32 field, u32 item) {
 AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
     u32 w[8];
     ge p;
-    load8(w, field_ptr(ws, (u32)j.field_a, item));
-    u32 ok = ge_decompress(p, w);
-    if (j.op != PJ_COPY) {
+    u32 ok = 1;
+    if (j.op == PJ_UNIFORM) {       // RistrettoPoint::random: 64 rng bytes through the Elligator map twice (amacs.rs:290)
+        u32 u[16];
+        load8(u, field_ptr(ws, (u32)j.field_a, item)); load8(u + 8, field_ptr(ws, (u32)j.field_b, item));
+        p = ge_from_uniform(u);
+    } else {
+        load8(w, field_ptr(ws, (u32)j.field_a, item));
+        ok = ge_decompress(p, w);
+    }
+    if (j.op == PJ_ADD || j.op == PJ_SUB) {
         ge q;
         load8(w, field_ptr(ws, (u32)j.field_b, item));
         ok &= ge_decompress(q, w);
@@ -178,8 +204,8 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
 
 // Constant-address table reads: every entry is loaded and the wanted one kept with masks, so neither the branch
 // pattern nor the address stream depends on the (secret) digit.
-AFX_HD pniels pniels_scan_select(const u32* table, int digit) {
-    u32 neg = (u32)digit >> 31;
+AFX_HD pniels pniels_scan_select(const u32* table, int digit, u32 xneg = 0) {
+    u32 neg = ((u32)digit >> 31) ^ xneg;
     u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
 #ifdef AFX_EXPERIMENT_DIRECT
     { pniels r = pniels_identity(); if (mag) r = load_pniels(table + 32 * (mag - 1)); return pniels_cneg(r, neg); }
@@ -200,8 +226,8 @@ AFX_HD pniels pniels_scan_select(const u32* table, int digit) {
     for (int i = 0; i < 8; i++) { r.YpX.v[i] = out[i]; r.YmX.v[i] = out[8 + i]; r.Z.v[i] = out[16 + i]; r.T2d.v[i] = out[24 + i]; }
     return pniels_cneg(r, neg);
 }
-AFX_HD aniels aniels_scan_select8(const u32* ctab, int digit) {
-    u32 neg = (u32)digit >> 31;
+AFX_HD aniels aniels_scan_select8(const u32* ctab, int digit, u32 xneg = 0) {
+    u32 neg = ((u32)digit >> 31) ^ xneg;
     u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
     u32 out[24];
     for (int comp = 0; comp < 3; comp++) {
@@ -314,6 +340,74 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
     if (active) store8(commit_ptr(ws, d.out_slot, item), w);
 }
 
+// ---- stage: constant-schedule msm (Issuer::issue) ----------------------------------------------------------------
+// Same job shape as msm_job but every scalar is a secret (issuer key material, per-item blindings, t): all terms use
+// radix-16 digits, no digit is skipped and table entries are fetched by scan-and-mask, so neither the instruction
+// stream nor the address stream depends on a scalar (dalek's constant-time `*` / multiscalar_mul, amacs.rs:267-270,
+// zkp prove_compact).  scratch: (nvar + ncon) * 8 words per item.
+AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, bool active = true) {
+    for (u32 k = 0; k < (u32)d.nvar + d.ncon; k++) {
+        u32 rec[8];
+        sc_recode16(rec, eval_scalar(ws, k < d.nvar ? d.var[k].s : d.con[k - d.nvar].s, item));
+        for (int w = 0; w < 8; w++) scratch[(k * 8 + w) * scratch_stride] = rec[w];
+    }
+    ge acc = ge_identity();
+    for (int i = 63; i >= 0; i--) {
+#if defined(__CUDA_ARCH__)
+        AFX_STEP_SYNC();
+#endif
+        if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+        for (u32 k = 0; k < d.nvar; k++) {
+            u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
+            int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
+            pniels e = pniels_scan_select(table_ptr(ws, d.var[k].table_slot, item), dig, d.var[k].neg);
+            acc = ge_add_pn(acc, e, true);
+        }
+        for (u32 k = 0; k < d.ncon; k++) {
+            u32 word = scratch[((d.nvar + k) * 8 + (i >> 3)) * scratch_stride];
+            int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
+            aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.con[k].ctab * CTAB_ENTRIES * 24, dig, d.con[k].neg);
+            acc = ge_madd(acc, e, true);
+        }
+    }
+    for (u32 k = 0; k < ((u32)d.nvar + d.ncon) * 8; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded secrets
+    if (d.flags & MSM_ADD_W) acc = ge_add_pn(acc, load_pniels(ws.W_pniels));
+    u32 w[8];
+    ge_compress(w, acc);
+    if (active) store8(commit_ptr(ws, d.out_slot, item), w);
+}
+
+// ---- stage: derived scalars (Issuer::issue) ------------------------------------------------------------------------
+// Scalar::random(rng) = 64 rng bytes reduced mod l (amacs.rs:289; zkp prove_compact's blindings)
+AFX_HD void derive_job(const Workspace& ws, const WideDesc& d, u32 slot, u32 item) {
+    u32 x[16];
+    load8(x, field_ptr(ws, d.lo, item)); load8(x + 8, field_ptr(ws, d.hi, item));
+    sc r = sc_reduce512(x);
+    store8(ws.derived + ((size_t)slot * ws.count + item) * 8, r.v);
+}
+
+// ---- stage: issuance output ----------------------------------------------------------------------------------------
+// word 0 = t, 1 = U, 2 = V, 3 = challenge, 4 + k = response k = witness_k * c + blinding_k (zkp prove_compact).
+// A request the Rust types could never hold (status != 0) yields all-zero words.
+AFX_HD void issue_out_job(const Workspace& ws, const IssueOutDesc& d, u32 word, u32 item, u32* out /*[nresp+4][count][8]*/) {
+    u32 w[8];
+    if (ws.status[item] != 0) { for (int i = 0; i < 8; i++) w[i] = 0; }
+    else if (word == 0) load8(w, scalar_ref_ptr(ws, SREF_DERIVED | d.der_t, item));
+    else if (word == 1) load8(w, comp_ptr(ws, d.comp_U, item));
+    else if (word == 2) load8(w, commit_ptr(ws, d.commit_V, item));
+    else if (word == 3) load8(w, ws.chal + (size_t)item * 8);
+    else {
+        u32 k = word - 4;
+        sc c = load_sc(ws.chal + (size_t)item * 8);
+        sc b = load_sc(scalar_ref_ptr(ws, SREF_DERIVED | d.resp_blind[k], item));
+        sc s;
+        if (d.resp_sec[k] == 0xffff) { s = sc_zero(); s.v[0] = 1; } else s = load_sc(ws.secsc + 8 * d.resp_sec[k]);
+        sc r = sc_muladd(s, c, b);
+        for (int i = 0; i < 8; i++) w[i] = r.v[i];
+    }
+    store8(out + ((size_t)word * ws.count + item) * 8, w);
+}
+
 // ---- stage: transcript -------------------------------------------------------------------------------------------
 AFX_HD const u32* tx_src(const Workspace& ws, u32 kind, u32 idx, u32 item) {
     if (kind == SRC_FIELD) return field_ptr(ws, idx, item);
@@ -351,8 +445,10 @@ AFX_HD void transcript_job(const Workspace& ws, const TxDesc& d, u32 item) {
     u32 x[16];
     for (int i = 0; i < 8; i++) { x[2 * i] = (u32)st[i]; x[2 * i + 1] = (u32)(st[i] >> 32); }
     sc c = sc_reduce512(x);
-    sc claimed = sc_from_words(field_ptr(ws, d.chal_field, item));
-    if (!sc_equal(c, claimed)) status_or(ws, item, ST_CHALLENGE);
+    if (d.chal_field != 0xffff) {      // verifier: compare with the claimed challenge; prover (Issuer::issue): just emit it
+        sc claimed = sc_from_words(field_ptr(ws, d.chal_field, item));
+        if (!sc_equal(c, claimed)) status_or(ws, item, ST_CHALLENGE);
+    }
     if (ws.chal) store8(ws.chal + ((size_t)d.out_slot * ws.count + item) * 8, c.v);
 }
 

@@ -106,8 +106,9 @@ struct TxBuilder {
     void point_var_const(const char* label, const uint8_t enc[32]) {  // per-issuer constant: identity checked at ctx creation
         append_message("ptvar", label, std::strlen(label)); append_message("val", enc, 32);
     }
-    void point_var(const char* label, u32 kind, u32 idx) {  // validate_and_append_point_var
-        TxIdCheck c; c.src_kind = (u16)kind; c.src_idx = (u16)idx; ids.push_back(c);
+    // verifier: validate_and_append_point_var (identity rejected); prover: append_point_var (no check)
+    void point_var(const char* label, u32 kind, u32 idx, bool check_identity = true) {
+        if (check_identity) { TxIdCheck c; c.src_kind = (u16)kind; c.src_idx = (u16)idx; ids.push_back(c); }
         append_message("ptvar", label, std::strlen(label));
         append_header("val", 32); begin_op(2, false); absorb_hole(kind, idx);
     }
@@ -127,6 +128,9 @@ struct TxBuilder {
 // ---- compiled program --------------------------------------------------------------------------------
 struct ShapeProgram {
     u32 n_fields = 0, n_tables = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
+    bool is_issue = false;             // Issuer::issue: constant-schedule MSMs, derived scalars, output words instead of verdicts
+    std::vector<WideDesc> derived;
+    IssueOutDesc issue_out{};
     std::vector<u16> scalar_fields;
     std::vector<PointJob> point_jobs;
     bool has_amac = false;
@@ -140,6 +144,8 @@ struct ShapeProgram {
     std::vector<u32> dump_commit; // commit slots that are blinding commitments, in constraint order (debug dump)
 };
 
+inline u32 sref_secret(u32 row) { return SREF_SECRET | row; }
+inline u32 sref_derived(u32 slot) { return SREF_DERIVED | slot; }
 inline ScalarSrc sc_field(u32 f) { ScalarSrc s; s.op = SC_FIELD; s.f0 = (u16)f; s.f1 = s.f2 = 0; return s; }
 inline ScalarSrc sc_mul2(u32 a, u32 b) { ScalarSrc s; s.op = SC_MUL; s.f0 = (u16)a; s.f1 = (u16)b; s.f2 = 0; return s; }
 inline ScalarSrc sc_muladd3(u32 a, u32 b, u32 c) { ScalarSrc s; s.op = SC_MULADD; s.f0 = (u16)a; s.f1 = (u16)b; s.f2 = (u16)c; return s; }
@@ -369,6 +375,93 @@ inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const
     tb.challenge();
     finish_transcript(P, tb, F_CHAL, 0);
     P.n_msm = slot; P.n_proofs = 1;
+    return P;
+}
+
+
+// Issuer::issue as a program (issuer.rs:111-124: Amac::tag amacs.rs:276-294 + ProofOfIssuance::prove issuance.rs:40-129),
+// with the rng output supplied by the caller.  kinds: 0 = scalar attribute, 2 = point attribute.
+// Fields: attr[n], then two 32-byte words (the 64 rng bytes) per random value: t, U, blinding[n+5] in the order the
+// witnesses are allocated (w, w', x_0, x_1, y[n], "1"; issuance.rs:52-68).  Output words: t, U, V, challenge, responses[n+5].
+inline size_t issue_num_fields(u32 n) { return (size_t)n + 2 * ((size_t)n + 7); }
+inline ShapeProgram compile_issue(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+    if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");  // amacs.rs:285-287
+    for (u32 i = 0; i < n; i++) if (kinds[i] != 0 && kinds[i] != 2) throw std::invalid_argument("bad request kind");
+    ShapeProgram P; P.is_issue = true;
+    const u32 F_ATTR = 0, F_TSEED = n, F_USEED = n + 2, F_BSEED = n + 4;
+    P.n_fields = (u32)issue_num_fields(n);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) P.scalar_fields.push_back((u16)(F_ATTR + i));
+    // derived scalars: slot 0 = t, 1 + k = blinding k
+    const u32 D_T = 0;
+    auto D_B = [](u32 k) { return 1 + k; };
+    { WideDesc w; w.lo = (u16)F_TSEED; w.hi = (u16)(F_TSEED + 1); P.derived.push_back(w); }
+    for (u32 k = 0; k < n + 5; k++) { WideDesc w; w.lo = (u16)(F_BSEED + 2 * k); w.hi = (u16)(F_BSEED + 2 * k + 1); P.derived.push_back(w); }
+    const u32 B_w = D_B(0), B_wp = D_B(1), B_x0 = D_B(2), B_x1 = D_B(3), B_one = D_B(4 + n);
+    auto B_y = [&](u32 i) { return D_B(4 + i); };
+    const u32 S_w = sref_secret(2 + n), S_wp = sref_secret(3 + n), S_x0 = sref_secret(sec_x0()), S_x1 = sref_secret(sec_x1());
+    (void)S_w; (void)S_wp;
+    // points: U = from_uniform(seed) with its ladder table and encoding; one ladder table per point attribute
+    u32 ntab = 0, ncomp = 0;
+    u32 T_U, C_U;
+    { PointJob j; j.field_a = (int16_t)F_USEED; j.field_b = (int16_t)(F_USEED + 1); j.op = PJ_UNIFORM; j.pad = 0; j.table_slot = (int16_t)(T_U = ntab++);
+      j.ext_slot = -1; j.comp_slot = (int16_t)(C_U = ncomp++); j.compneg_slot = -1; P.point_jobs.push_back(j); }
+    std::vector<int> T_M(n, -1);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 2) {
+        PointJob j; j.field_a = (int16_t)(F_ATTR + i); j.field_b = -1; j.op = PJ_COPY; j.pad = 0; j.table_slot = (int16_t)(T_M[i] = (int)ntab++);
+        j.ext_slot = -1; j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j);
+    }
+    P.n_tables = ntab; P.n_ext = 0; P.n_comp = ncomp;
+    u32 slot = 0;
+    auto D = [](u32 d) { return sc_field(sref_derived(d)); };
+    // M_i = m_i * G_m[i] (amacs.rs:234-235), tU = t * U (issuance.rs:91)
+    std::vector<int> S_M(n, -1);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) { MsmBuilder m(slot); m.con(ic.id_Gm(i), sc_field(F_ATTR + i)); P.msms.push_back(m.d); S_M[i] = (int)slot++; }
+    u32 S_tU; { MsmBuilder m(slot); m.var(T_U, D(D_T)); P.msms.push_back(m.d); S_tU = slot++; }
+    // V = W + x_0*U + (x_1*t)*U + sum y_i*M_i (amacs.rs:267-270), as one ladder: (x_0 + x_1*t)*U + sum (y_i*m_i)*G_m[i] + sum y_i*M_i, then + W
+    u32 S_V;
+    { MsmBuilder m(slot); m.d.flags = MSM_ADD_W;
+      m.var(T_U, sc_muladd3(S_x0, S_x1, sref_derived(D_T)));
+      for (u32 i = 0; i < n; i++) {
+          if (kinds[i] == 0) m.con(ic.id_Gm(i), sc_mul2(sref_secret(sec_y(i)), F_ATTR + i));
+          else m.var((u32)T_M[i], sc_field(sref_secret(sec_y(i))));
+      }
+      P.msms.push_back(m.d); S_V = slot++; }
+    // blinding commitments of the three constraints (issuance.rs:106-126; zkp prove_compact)
+    u32 S_CW, S_I, S_CV;
+    { MsmBuilder m(slot); m.con(ic.id_Gw(), D(B_w)); m.con(ic.id_Gwp(), D(B_wp)); P.msms.push_back(m.d); S_CW = slot++; }
+    { MsmBuilder m(slot); m.con(ic.id_GV(), D(B_one)); m.con(ic.id_Gx0(), D(B_x0), true); m.con(ic.id_Gx1(), D(B_x1), true);
+      for (u32 i = 0; i < n; i++) m.con(ic.id_Gy(i), D(B_y(i)), true);
+      P.msms.push_back(m.d); S_I = slot++; }
+    { MsmBuilder m(slot); m.con(ic.id_Gw(), D(B_w));
+      m.var(T_U, sc_muladd3(sref_derived(B_x0), sref_derived(B_x1), sref_derived(D_T)));      // b_x0*U + b_x1*(t*U)
+      for (u32 i = 0; i < n; i++) {
+          if (kinds[i] == 0) m.con(ic.id_Gm(i), sc_mul2(sref_derived(B_y(i)), F_ATTR + i));    // b_y_i * (m_i*G_m[i])
+          else m.var((u32)T_M[i], D(B_y(i)));
+      }
+      P.msms.push_back(m.d); S_CV = slot++; }
+    TxBuilder tb; tb.start("2019/1416 anonymous credential"); tb.domain_sep("2019/1416 issuance proof");
+    tb.scalar_var("w"); tb.scalar_var("w'"); tb.scalar_var("x_0"); tb.scalar_var("x_1");
+    for (u32 i = 0; i < n; i++) tb.scalar_var("y");
+    tb.scalar_var("1");
+    tb.point_var_const("G_V", ic.enc[ic.id_GV()].data()); tb.point_var_const("G_w", ic.enc[ic.id_Gw()].data());
+    tb.point_var_const("G_w_prime", ic.enc[ic.id_Gwp()].data());
+    tb.point_var_const("-G_x_0", ic.enc_neg[ic.id_Gx0()].data()); tb.point_var_const("-G_x_1", ic.enc_neg[ic.id_Gx1()].data());
+    for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("-G_y", ic.enc_neg[ic.id_Gy(i)].data());
+    tb.point_var_const("C_W", ic.enc[ic.id_CW()].data()); tb.point_var_const("I", ic.enc[ic.id_I()].data());
+    tb.point_var("U", SRC_COMP, C_U, false); tb.point_var("V", SRC_COMMIT, S_V, false); tb.point_var("tU", SRC_COMMIT, S_tU, false);
+    for (u32 i = 0; i < n; i++) { if (kinds[i] == 0) tb.point_var("M", SRC_COMMIT, (u32)S_M[i], false); else tb.point_var("M", SRC_FIELD, F_ATTR + i, false); }
+    tb.blinding_commitment("C_W", S_CW); tb.blinding_commitment("I", S_I); tb.blinding_commitment("V", S_CV);
+    for (u32 s : {S_CW, S_I, S_CV}) P.dump_commit.push_back(s);
+    tb.challenge();
+    finish_transcript(P, tb, 0xffff, 0);
+    P.n_msm = slot; P.n_proofs = 1;
+    IssueOutDesc& O = P.issue_out; std::memset(&O, 0, sizeof O);
+    O.nresp = (u16)(n + 5); O.comp_U = (u16)C_U; O.commit_V = (u16)S_V; O.der_t = (u16)D_T;
+    const u32 rows[4] = {2 + n, 3 + n, sec_x0(), sec_x1()};
+    for (u32 k = 0; k < 4; k++) O.resp_sec[k] = (u16)rows[k];
+    for (u32 i = 0; i < n; i++) O.resp_sec[4 + i] = (u16)sec_y(i);
+    O.resp_sec[4 + n] = 0xffff;
+    for (u32 k = 0; k < n + 5; k++) O.resp_blind[k] = (u16)D_B(k);
     return P;
 }
 

@@ -8,6 +8,8 @@
     Issuer::verify(&self, &presentation) issuer.rs:141-147  Issuer.verify_batch(PresentationBatch) -> verdicts
     CredentialIssuance::verify(self, &sp, &ip)              Issuer.verify_issuance_batch(IssuanceBatch) -> verdicts
                                          issuer.rs:48-57      (amacs_key=None suffices: it is the user-side check)
+    Issuer::issue(&self, request, &mut rng)                 Issuer.issue_batch(RequestBatch) -> (IssuanceBatch, status)
+                                         issuer.rs:111-124    (the rng output is part of the request batch)
     Result<(), CredentialError::VerificationFailure>        verdict 0 / 1 per item (errors.rs:152-156)
 
 The reference defines no wire format for presentations or issuances (presentation.rs:117 "XXX"); the flat
@@ -42,6 +44,24 @@ class PresentationBatch:
 
 
 IssuanceBatch = PresentationBatch   # same container; kinds are 0 (scalar attribute) / 2 (point attribute)
+
+
+class RequestBatch(PresentationBatch):
+    """A batch of CredentialRequests (user.rs:137-139) plus the rng output Issuer::issue would draw for each.
+
+    fields [3n + 14][count][32]: attribute[n], then the low/high 32 bytes of the 64 rng bytes behind t, U and each of the
+    n + 5 proof blindings (include/aeonflux_b200.h)."""
+
+    @staticmethod
+    def from_request(kinds, attributes, randomness):
+        """attributes: uint8 [count][n][32]; randomness: uint8 [count][n + 7][64] (t, U, blinding[n + 5])."""
+        attributes = np.asarray(attributes, dtype=np.uint8)
+        randomness = np.asarray(randomness, dtype=np.uint8)
+        count, n = attributes.shape[0], len(kinds)
+        if attributes.shape != (count, n, 32) or randomness.shape != (count, n + 7, 64):
+            raise ValueError("attributes must be [count][n][32] and randomness [count][n+7][64]")
+        items = np.concatenate([attributes, randomness.reshape(count, 2 * (n + 7), 32)], axis=1)
+        return RequestBatch(kinds, np.ascontiguousarray(items.transpose(1, 0, 2)))
 
 
 class Issuer:
@@ -125,6 +145,36 @@ class Issuer:
     def verify_issuance_batch(self, batch: IssuanceBatch, debug=False):
         """Batch CredentialIssuance::verify (issuer.rs:48-57)."""
         return self._run(self._b.L.afx_verify_issuances, batch, 3, 1, debug)
+
+    def issue_batch(self, batch: RequestBatch, debug=False):
+        """Batch Issuer::issue (issuer.rs:111-124).  Returns (IssuanceBatch, status): the issuances in the layout
+        verify_issuance_batch takes (attribute[n], t, U, V, challenge, responses[n+5]); status 0 = Ok, 1 = malformed request."""
+        n, count = len(batch.kinds), batch.count
+        if batch.fields.shape[0] != 3 * n + 14:
+            raise ValueError("a request batch has 3n + 14 fields")
+        ptrs, keep = B._as_fields(batch.fields)
+        cb = B.afx_presentation_batch(n, batch.kinds, count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        out = np.zeros((2 * n + 9, count, 32), np.uint8)
+        out[:n] = batch.fields[:n]
+        optrs, okeep = B._as_fields(out[n:])
+        ob = B.afx_issuance_out(ctypes.cast(optrs, ctypes.POINTER(ctypes.c_void_p)), len(okeep))
+        status = np.zeros(count, np.uint8)
+        dbg, dump = None, None
+        if debug:
+            dump = {"commitments": np.zeros((3, count, 32), np.uint8), "status": np.zeros(count, np.uint32)}
+            dbg = B.afx_debug_dump(None, dump["commitments"].ctypes.data, None, dump["status"].ctypes.data)
+        self._b.check(self._b.L.afx_issue(self._h, ctypes.byref(cb), ctypes.byref(ob), status.ctypes.data, ctypes.byref(dbg) if dbg is not None else None))
+        for i, a in enumerate(okeep):            # _as_fields may have copied non-contiguous rows
+            if a is not out[n + i] and not np.shares_memory(a, out):
+                out[n + i] = a
+        res = IssuanceBatch(batch.kinds, out)
+        return (res, status, dump) if debug else (res, status)
+
+    def issue_batch_device(self, kinds, count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream=0):
+        self._b.check(self._b.L.afx_issue_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream))
+
+    def verify_issuance_batch_device(self, kinds, count, fields_dev_ptr, verdicts_dev_ptr, stream=0):
+        self._b.check(self._b.L.afx_verify_issuances_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, verdicts_dev_ptr, stream))
 
     def verify_batch_device(self, kinds, count, fields_dev_ptr, verdicts_dev_ptr, stream=0):
         """Enqueue Issuer::verify for a batch already in device memory ([n_fields][count][32]); no synchronisation."""

@@ -97,6 +97,46 @@ typedef struct {
 /* Batch CredentialIssuance::verify (src/issuer.rs:48-57 -> src/nizk/issuance.rs:132-218).  Needs no secret key. */
 int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
 
+/* Same as afx_verify_issuances with the batch resident on the device ([2*n_attrs + 9][count][32] contiguous). */
+int afx_verify_issuances_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev,
+                                void* verdicts_dev, void* stream);
+
+/* Batch Issuer::issue (src/issuer.rs:111-124 = Amac::tag, src/amacs.rs:276-294, + ProofOfIssuance::prove,
+ * src/nizk/issuance.rs:40-129).  The reference draws t, U and the proof's blindings from the caller's rng
+ * (`&mut rng` argument / zkp's TranscriptRng); here the caller passes that rng output explicitly, 64 bytes per random
+ * value exactly as Scalar::random / RistrettoPoint::random consume them, so that the result is a deterministic function
+ * of its inputs (and byte-identical to the reference given the same rng bytes).
+ *
+ * Request fields for request kinds k[0..n) (0 = scalar attribute, 2 = point attribute -- a revealed point or the M1 of a
+ * plaintext): attribute[n], then two 32-byte words (low, high half of the 64 rng bytes) for each of
+ *     t, U, blinding[n + 5]   (blindings in witness order w, w', x_0, x_1, y[n], "1"; src/nizk/issuance.rs:52-68)
+ * i.e. 3*n + 14 fields.  Output fields: t, U, V, challenge, responses[n + 5]  (n + 9 fields, each [count][32]) -- together
+ * with the request's attribute fields this is exactly the afx_issuance_batch layout, so an issued batch can be handed to
+ * afx_verify_issuances unchanged.  status: 0 = Ok, 1 = the request holds bytes the Rust types could never hold
+ * (undecodable point / scalar >= l); its output words are all-zero.  An attribute count different from the issuer's is
+ * AFX_ERR_SHAPE for the whole call (CredentialError::MacCreation, src/amacs.rs:285-287).
+ * Every scalar on this path is secret (key material, blindings, t): all ladders run a constant schedule with
+ * constant-address table scans (dalek's constant-time `*` and multiscalar_mul). */
+typedef struct {
+    uint16_t n_attrs;
+    const uint8_t* kinds;          /* [n_attrs] 0 = scalar attribute, 2 = point attribute */
+    size_t count;
+    const uint8_t* const* fields;  /* [3*n_attrs + 14] pointers, each to [count][32] bytes */
+    size_t n_fields;               /* must equal afx_request_num_fields(n_attrs) */
+} afx_request_batch;
+
+typedef struct {
+    uint8_t* const* fields;        /* [n_attrs + 9] pointers, each to [count][32] bytes: t, U, V, challenge, responses[n+5] */
+    size_t n_fields;
+} afx_issuance_out;
+
+size_t afx_request_num_fields(uint16_t n_attrs);
+/* dbg (nullable): commitments = the three blinding commitments [3][count][32]; status. */
+int afx_issue(afx_ctx* ctx, const afx_request_batch* batch, const afx_issuance_out* out, uint8_t* status, afx_debug_dump* dbg);
+/* Device-resident variant: fields_dev = [3*n_attrs + 14][count][32], out_dev = [n_attrs + 9][count][32], status_dev = [count]. */
+int afx_issue_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
+                     void* status_dev, void* stream);
+
 /* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */
 uint64_t afx_launch_count(const afx_ctx* ctx);
 

@@ -83,3 +83,16 @@ def corrupt_batch(pres, kinds, rng, fraction, oracle_points):
         else:
             sc_plus1(1)
     return idx
+
+
+def golden_issue_request(g, entry):
+    """Rebuild the CredentialRequest and the rng output behind a golden item's issuance: oracle/pyoracle/synth.py draws
+    the attributes, then t, U and the n+5 blindings (64 bytes each) from SHAKE-256(prefix || config || item)."""
+    from oracle.pyoracle import aeonflux as A, synth as S
+    rng = S.item_rng(g["config"].encode(), entry["item"])
+    for k in g["request"]:
+        rng.fill(30 if k == "EP" else 64)
+    n = g["n"]
+    rnd = np.frombuffer(rng.fill(64 * (n + 7)), np.uint8).reshape(n + 7, 64).copy()
+    attrs = words(entry["issuance_words"][:n])
+    return attrs, rnd

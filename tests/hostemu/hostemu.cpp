@@ -47,6 +47,16 @@ static void be_launch_msm(const Workspace& ws, const MsmDesc* msms, const u32* i
         for (u32 i = 0; i < ws.count; i++) msm_job(ws, d, i, scratch.data(), 1, r);
     }
 }
+static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* msms, const u32* idx, u32 nidx, u32 max_terms, be_stream) {
+    std::vector<u32> scratch((size_t)max_terms * 8);
+    for (u32 k = 0; k < nidx; k++) for (u32 i = 0; i < ws.count; i++) msm_ct_job(ws, msms[idx[k]], i, scratch.data(), 1);
+}
+static void be_launch_derive(const Workspace& ws, const WideDesc* d, u32 nd, be_stream) {
+    for (u32 k = 0; k < nd; k++) for (u32 i = 0; i < ws.count; i++) derive_job(ws, d[k], k, i);
+}
+static void be_launch_issue_out(const Workspace& ws, const IssueOutDesc* d, u32 nwords, u32* out, be_stream) {
+    for (u32 k = 0; k < nwords; k++) for (u32 i = 0; i < ws.count; i++) issue_out_job(ws, *d, k, i, out);
+}
 static void be_launch_transcript(const Workspace& ws, const TxDesc* txs, u32 ntx, be_stream) {
     for (u32 k = 0; k < ntx; k++) for (u32 i = 0; i < ws.count; i++) transcript_job(ws, txs[k], i);
 }

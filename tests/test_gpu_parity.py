@@ -149,3 +149,65 @@ def test_full_size_batch_round_trip_properties(readme4):
     sample = np.concatenate([bad[:64], rng.choice(65536, 64, replace=False)])
     ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(big[sample]))
     assert (v[sample] == ov).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SHAPES)
+def test_issue_golden_shapes(coracle, name):
+    """Issuer::issue (issuer.rs:111-124) on the GPU with supplied rng output: the committed Python-oracle fixture, then a
+    ragged batch against the C oracle, including malformed requests; every issued credential verifies."""
+    from aeonflux_b200 import Issuer, RequestBatch
+    from tests.common import golden_issue_request
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    n = g["n"]
+    iss = Issuer(sp, ip, sk, device=0, max_batch=64)
+    e = g["items"][0]
+    ik = bytes(e["issuance_kinds"])
+    attrs, rnd = golden_issue_request(g, e)
+    res, st, dbg = iss.issue_batch(RequestBatch.from_request(ik, attrs[None], rnd[None]), debug=True)
+    assert st[0] == 0
+    assert res.fields[:, 0].tobytes().hex() == "".join(e["issuance_words"])
+    assert dbg["commitments"][:, 0].tobytes().hex() == "".join(e["issuance_commitments"])
+    orc = coracle.Issuer(sp, ip, sk)
+    rk = bytes(REQ[k] for k in g["request"])
+    count = 70
+    _, _, issu = orc.synth(rk, [], g["config"].encode() + b"-issue", 0, count)
+    A = np.ascontiguousarray(issu[:, :n])
+    R = np.random.default_rng(21).integers(0, 256, (count, n + 7, 64), dtype=np.uint8)
+    A[5, 0] = 0xff
+    A[33, n - 1, 0] ^= 1
+    out, status, _ = orc.issue(ik, A, R)
+    res, st = iss.issue_batch(RequestBatch.from_request(ik, A, R))
+    assert (st == status).all() and status[5] == 1
+    assert (res.fields.transpose(1, 0, 2)[:, n:] == out).all()
+    v = iss.verify_issuance_batch(res)
+    ov, _ = orc.verify_issuances(ik, np.ascontiguousarray(res.fields.transpose(1, 0, 2)))
+    assert (v == ov).all() and (v[status == 1] == 1).all()
+
+
+def test_issue_full_size_round_trip(readme4):
+    """BASELINE config 3 size: 65,536 revealed 4-attribute requests through issue -> CredentialIssuance::verify on the
+    device; every honest issuance verifies, a sample is byte-identical to the oracle, and flipping a bit of an issued
+    word makes exactly that item fail."""
+    from aeonflux_b200 import Issuer, RequestBatch
+    orc, _, (sp, ip, sk) = readme4
+    count = 65536
+    kinds = bytes([0, 0, 2, 2])
+    _, _, issu = orc.synth(b"SSPP", [], b"issue-full", 0, 2048)
+    A = np.tile(np.ascontiguousarray(issu[:, :4]), (count // 2048, 1, 1))
+    R = np.random.default_rng(22).integers(0, 256, (count, 11, 64), dtype=np.uint8)
+    iss = Issuer(sp, ip, sk, device=0, max_batch=count)
+    res, st = iss.issue_batch(RequestBatch.from_request(kinds, A, R))
+    assert not st.any()
+    sample = np.random.default_rng(23).choice(count, 128, replace=False)
+    out, status, _ = orc.issue(kinds, np.ascontiguousarray(A[sample]), np.ascontiguousarray(R[sample]))
+    assert (res.fields.transpose(1, 0, 2)[sample, 4:] == out).all()
+    bad = np.random.default_rng(24).choice(count, 300, replace=False)
+    rr = np.random.default_rng(25)
+    for i in bad:
+        w = 4 + rr.integers(0, 13)
+        res.fields[w, i, rr.integers(0, 31)] ^= 1 << rr.integers(0, 8)
+    v = iss.verify_issuance_batch(res)
+    expect = np.zeros(count, np.uint8)
+    expect[bad] = 1
+    assert (v == expect).all()

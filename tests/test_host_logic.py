@@ -90,6 +90,63 @@ def test_stage_logic_matches_oracle_on_golden_shapes(emu, coracle, name):
     assert (user.verify_issuance_batch(PresentationBatch.from_items(ik, issu)) == ovi).all()
 
 
+@pytest.mark.parametrize("name", GOLDEN_SHAPES)
+def test_issue_stage_logic_matches_golden_and_oracle(emu, coracle, name):
+    """Issuer::issue (issuer.rs:111-124) with supplied rng output: byte-identical to the Python oracle's committed
+    fixture and to the C oracle on fresh randomness; malformed requests; the result verifies."""
+    from aeonflux_b200 import Issuer, RequestBatch
+    from tests.common import golden_issue_request, words
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    n = g["n"]
+    iss = Issuer(sp, ip, sk, max_batch=3, _binding=emu)
+    e = g["items"][0]
+    ik = bytes(e["issuance_kinds"])
+    attrs, rnd = golden_issue_request(g, e)
+    res, st, dbg = iss.issue_batch(RequestBatch.from_request(ik, attrs[None], rnd[None]), debug=True)
+    assert st[0] == 0
+    assert res.fields[:, 0].tobytes().hex() == "".join(e["issuance_words"])
+    assert dbg["commitments"][:, 0].tobytes().hex() == "".join(e["issuance_commitments"])   # prover's blinding commitments == verifier's
+    # fresh randomness, 5 items (two chunks), one malformed scalar or point
+    orc = coracle.Issuer(sp, ip, sk)
+    rng = np.random.default_rng(11)
+    A = np.repeat(attrs[None], 5, axis=0)
+    R = rng.integers(0, 256, (5, n + 7, 64), dtype=np.uint8)
+    A[3, 0] = 0xff
+    out, status, _ = orc.issue(ik, A, R)
+    res, st = iss.issue_batch(RequestBatch.from_request(ik, A, R))
+    assert (st == status).all() and list(status) == [0, 0, 0, 1, 0]
+    assert (res.fields.transpose(1, 0, 2)[:, n:] == out).all()
+    assert list(iss.verify_issuance_batch(res)) == [0, 0, 0, 1, 0]
+
+
+def test_issue_edges(emu, coracle):
+    from aeonflux_b200 import Issuer, RequestBatch
+    from aeonflux_b200._binding import AfxError
+    sp, ip, sk = coracle.make_issuer(4)
+    iss = Issuer(sp, ip, sk, max_batch=8, _binding=emu)
+    kinds = bytes([0, 0, 2, 2])
+    res, st = iss.issue_batch(RequestBatch(kinds, np.zeros((26, 0, 32), np.uint8)))            # empty
+    assert res.count == 0 and len(st) == 0
+    with pytest.raises(AfxError):                                                              # amacs.rs:285-287: wrong attribute count
+        iss.issue_batch(RequestBatch(bytes([0, 0, 2]), np.zeros((23, 1, 32), np.uint8)))
+    with pytest.raises(AfxError):                                                              # hidden kinds cannot be issued
+        iss.issue_batch(RequestBatch(bytes([0, 1, 2, 3]), np.zeros((26, 1, 32), np.uint8)))
+    user = Issuer(sp, ip, None, max_batch=8, _binding=emu)
+    with pytest.raises(AfxError):
+        user.issue_batch(RequestBatch(kinds, np.zeros((26, 1, 32), np.uint8)))
+    # an all-zero 30-byte plaintext encodes to the identity (encoding.rs:55): issue succeeds, issuance verify rejects it
+    # (issuance.rs:271-295)
+    orc = coracle.Issuer(sp, ip, sk)
+    _, _, issu = orc.synth(b"SSPP", [], b"issue-edges", 0, 2)
+    A = np.ascontiguousarray(issu[:, :4]); A[1, 3] = 0
+    R = np.random.default_rng(3).integers(0, 256, (2, 11, 64), dtype=np.uint8)
+    res, st = iss.issue_batch(RequestBatch.from_request(kinds, A, R))
+    out, status, _ = orc.issue(kinds, A, R)
+    assert (res.fields.transpose(1, 0, 2)[:, 4:] == out).all() and not st.any()
+    assert list(iss.verify_issuance_batch(res)) == [0, 1]
+
+
 def test_corruption_classes_and_edges(emu, coracle):
     from aeonflux_b200 import Issuer, PresentationBatch
     from aeonflux_b200._binding import AfxError
