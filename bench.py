@@ -113,6 +113,71 @@ def cpu_leg(sp, ip, sk, items, sample, threads):
     return verdicts, sample / wall, wall
 
 
+
+def time_device(torch, stream, flush, fn, steps, warmup=2):
+    """Device ms per call of fn (enqueues on `stream`), L2 flushed before each timed call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); fn(); e1.record(stream)
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / steps
+
+
+def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, steps):
+    """BASELINE configs[2] and configs[3] on the same GPU (device-resident inputs, CUDA events): batch Issuer::issue and
+    CredentialIssuance::verify of B revealed 4-attribute requests, and Issuer::verify of S16 presentations.  Reported under
+    `secondary`; the headline stays configs[1]."""
+    from aeonflux_b200 import Issuer
+    out = {}
+    # ---- issuance: requests [scalar, scalar, point, point]; the point attributes are valid encodings taken from the fixture
+    kinds = bytes([0, 0, 2, 2])
+    rng = np.random.default_rng(1234)
+    n, nf = 4, 3 * 4 + 14
+    req = np.empty((nf, B, 32), np.uint8)
+    sc = rng.integers(0, 256, (2, B, 32), dtype=np.uint8); sc[:, :, 31] &= 0x0f       # < 2^252 < l: canonical scalars
+    req[0:2] = sc
+    req[2] = items4[:B, 5]; req[3] = items4[:B, 6]                                     # C_x_0, C_x_1 of the fixture: valid points
+    req[4:] = rng.integers(0, 256, (nf - 4, B, 32), dtype=np.uint8)                    # rng output for t, U, blindings
+    req_dev = torch.from_numpy(req).cuda()
+    iss_dev = torch.empty((2 * n + 9, B, 32), dtype=torch.uint8, device="cuda")
+    iss_dev[:n] = req_dev[:n]
+    status_dev = torch.empty(B, dtype=torch.uint8, device="cuda")
+    ms = time_device(torch, stream, flush, lambda: issuer4.issue_batch_device(kinds, B, req_dev.data_ptr(), iss_dev[n:].data_ptr(), status_dev.data_ptr(), stream.cuda_stream), steps)
+    assert int(status_dev.sum().item()) == 0
+    out["issue_4attr"] = {"workload": "batch Issuer::issue (Amac::tag + ProofOfIssuance::prove) of %d revealed 4-attribute requests (BASELINE configs[2])" % B,
+                          "value": B / (ms * 1e-3), "unit": "issuances/s", "ms_per_step": ms}
+    verdicts_dev = torch.empty(B, dtype=torch.uint8, device="cuda")
+    ms = time_device(torch, stream, flush, lambda: issuer4.verify_issuance_batch_device(kinds, B, iss_dev.data_ptr(), verdicts_dev.data_ptr(), stream.cuda_stream), steps)
+    assert int(verdicts_dev.sum().item()) == 0, "issued credentials failed CredentialIssuance::verify"
+    out["verify_issuance_4attr"] = {"workload": "batch CredentialIssuance::verify of the %d issuances above" % B,
+                                    "value": B / (ms * 1e-3), "unit": "issuances/s", "ms_per_step": ms}
+    # ---- S16 presentations (configs[3]); 16,384 per step keeps the 2.3 GB of ladder tables modest
+    try:
+        blob = open(os.path.join(ROOT, "bench_data", "issuer16.bin"), "rb").read()
+        pres = np.fromfile(os.path.join(ROOT, "bench_data", "s16_256.bin"), np.uint8).reshape(-1, 143, 32)
+    except OSError:
+        return out
+    sp, ip, sk = blob[:1316], blob[1316:1380], blob[1380:]
+    B16 = min(B, 16384)
+    k16 = bytes([1, 1, 0, 0, 0, 0, 2, 2] + [3] * 8)
+    issuer16 = Issuer(sp, ip, sk, device=local, max_batch=B16)
+    f16 = torch.from_numpy(np.ascontiguousarray(np.tile(pres, ((B16 + 255) // 256, 1, 1))[:B16].transpose(1, 0, 2))).cuda()
+    v16 = torch.empty(B16, dtype=torch.uint8, device="cuda")
+    ms = time_device(torch, stream, flush, lambda: issuer16.verify_batch_device(k16, B16, f16.data_ptr(), v16.data_ptr(), stream.cuda_stream), steps)
+    assert int(v16.sum().item()) == 0
+    wm = work_model(k16)
+    out["verify_s16"] = {"workload": "batch Issuer::verify of %d 16-attribute presentations, 8 hidden plaintext attributes (BASELINE configs[3])" % B16,
+                         "value": B16 / (ms * 1e-3), "unit": "presentations/s", "ms_per_step": ms,
+                         "pipeline_frac_of_imad_peak": (B16 * 2 * wm["total"] / (ms * 1e-3)) / (148 * 64 * 1965e6)}
+    issuer16.close()
+    return out
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU schedule of Issuer::verify on the host cores.  The Rust crate cannot be
     built in this image (no rustc/cargo, un-vendored deps), so this is the C restatement of its schedule (oracle/c)."""
@@ -120,7 +185,7 @@ def run_reference(args, rank):
         return
     cores = os.cpu_count() or 1
     sp, ip, sk, items = load_fixture(args.batch)
-    sample = max(cores * 64, 2048)
+    sample = min(args.batch, cores * 2048)          # ~2 s of work per step on every host core
     for _ in range(args.warmup):
         cpu_leg(sp, ip, sk, items, min(sample, cores * 16), cores)
     t_total, n_total = 0.0, 0
@@ -147,6 +212,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the issuance / S16 measurements (configs[2], configs[3])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -221,6 +287,10 @@ def main():
         assert not v.any()
     barrier()
 
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = secondary_measurements(torch, issuer, items, local, stream, flush, B, min(args.steps, 3))
+
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,9 +333,11 @@ def main():
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "presentations/s", "h2d_bytes_per_step": B * WORDS * 32, "d2h_bytes_per_step": B, "ms_per_step": e2e_ms_max / args.steps},
             "roofline": roofline}
+    if secondary:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = max(cores * 128, 4096)
+        sample = min(B, cores * 8192)                  # ~10 s of CPU work at ~1 k presentations/s/core
         cv, rate, wall = cpu_leg(sp, ip, sk, items, sample, cores)
         gv = issuer.verify_batch(PresentationBatch.from_items(kinds, items[:sample]))
         assert (cv == gv).all(), "GPU verdicts differ from the CPU restatement"

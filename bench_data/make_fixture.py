@@ -3,6 +3,8 @@ each, item-major) plus the issuer they verify under (bench_data/issuer4.bin = sy
 with the oracle's reference-schedule prover from the fixed SHAKE-256 seeds of SURVEY 8d (config "bench-readme4").
 bench.py tiles these to the 65,536-item batch of BASELINE config 2: every item is independent and every stage's control flow
 is data-independent, so tiling changes neither the work nor the memory traffic (each item still owns its own workspace rows).
+Also writes bench_data/s16_256.bin / issuer16.bin: 256 honest S16 presentations (kinds [SS,SS,PS,PS,PS,PS,PP,PP,SPx8], 143 words,
+BASELINE config 4) for bench.py's secondary measurements.
 Run from the repo root:  python bench_data/make_fixture.py"""
 import os
 import sys
@@ -19,4 +21,14 @@ v, _ = iss.verify_presentations(kinds, pres)
 assert not v.any()
 pres.tofile(os.path.join(HERE, "readme4_1024.bin"))
 open(os.path.join(HERE, "issuer4.bin"), "wb").write(sp + ip + sk)
+print("wrote", pres.shape, len(sp), len(ip), len(sk))
+
+sp, ip, sk = C.make_issuer(16)
+iss = C.Issuer(sp, ip, sk)
+kinds, pres, _ = iss.synth(b"SSSSSSPP" + b"E" * 8, [0, 1] + list(range(8, 16)), b"bench-s16", 0, 256, want_issuances=False)
+assert list(kinds) == [1, 1, 0, 0, 0, 0, 2, 2] + [3] * 8
+v, _ = iss.verify_presentations(kinds, pres)
+assert not v.any()
+pres.tofile(os.path.join(HERE, "s16_256.bin"))
+open(os.path.join(HERE, "issuer16.bin"), "wb").write(sp + ip + sk)
 print("wrote", pres.shape, len(sp), len(ip), len(sk))

@@ -48,17 +48,21 @@ def test_product_has_no_cpu_fallback():
         lib._binding, lib.SO_PATH = saved
 
 
-@pytest.fixture(scope="session")
-def emu():
-    """The host-emulation build of the same C ABI (tests only)."""
+def build_hostemu():
     d = os.path.join(ROOT, "tests", "hostemu")
     so, src = os.path.join(d, "libafx_hostemu.so"), os.path.join(d, "hostemu.cpp")
     csrc = os.path.join(ROOT, "aeonflux_b200", "csrc")
     newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc) if not f.endswith(".so"))
     if not os.path.exists(so) or os.path.getmtime(so) < max(newest, os.path.getmtime(src)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-x", "c++", "-o", so, src])
+    return so
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """The host-emulation build of the same C ABI (tests only)."""
     from aeonflux_b200._binding import Binding
-    return Binding(ctypes.CDLL(so))
+    return Binding(ctypes.CDLL(build_hostemu()))
 
 
 @pytest.mark.parametrize("name", GOLDEN_SHAPES)
