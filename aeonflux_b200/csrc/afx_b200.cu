@@ -14,7 +14,14 @@
 namespace afx {
 
 constexpr int TPB = 128;            // threads per CTA for the ladder kernels (4 warps, one per SMSP)
-constexpr int TPB_MSM = 512;        // one lockstep CTA per SM for the constraint ladders (16 warps share the I-cache)
+#ifndef AFX_TPB_MSM
+#define AFX_TPB_MSM 256
+#define AFX_MSM_MINB 2
+#endif
+// Ladder CTAs run in lockstep (a barrier per ladder step) so that their warps share instruction-cache lines.  Measured on
+// B200 (README-4, fused ladders): 1 x 512 threads/SM 24.4 ms, 2 x 256 23.6 ms (finer tail), 4 x 128 25.7 ms (I-cache misses return).
+constexpr int TPB_MSM = AFX_TPB_MSM;
+constexpr size_t LADDER_SMEM_BUDGET = (size_t)(200 / AFX_MSM_MINB) * 1024;   // per CTA, so that AFX_MSM_MINB CTAs fit one SM
 constexpr int MSM_STAGE_TABLES = 3; // constant-base tables staged in shared memory per CTA (12 KB each)
 
 __global__ void __launch_bounds__(256) k_scalar_check(Workspace ws, const u16* fields) {
@@ -27,33 +34,75 @@ __global__ void __launch_bounds__(TPB, 4) k_points(Workspace ws, const PointJob*
     if (item < ws.count) points_job(ws, jobs[blockIdx.y], item);
 }
 
-__global__ void __launch_bounds__(TPB, 4) k_amac(Workspace ws, const AmacDesc* d) {
-    extern __shared__ u32 smem[];
-    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < ws.count) amac_job(ws, *d, item, smem + threadIdx.x, blockDim.x);
+// All ladders of a verify pipeline in ONE launch: blockIdx.y = 0 is the aMAC ladder (when the shape has one), the rest are
+// the constraint MSMs.  The aMAC ladder is bound by its constant-address table scans (HBM), the MSMs by the IMAD pipe;
+// sharing a grid lets the SMs that run aMAC CTAs stream their tables while the others multiply, instead of every SM
+// contending for HBM at once.  The one MSM that consumes Z (constraint "Z", presentation.rs:416) is ordered last and waits
+// on a per-CTA completion flag written by the aMAC CTAs (release/acquire at gpu scope; CTAs are dispatched in block-index
+// order, so the producers are always scheduled before any consumer).
+__device__ __forceinline__ u32 ld_acquire(const u32* p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+struct LadderArgs {
+    const MsmDesc* msms; const u32* group_idx; u32 scratch_terms;
+    const AmacDesc* amac;     // nullable
+    u32* flags; u32 epoch; u32 flag_tpb; int dep_msm;   // MSM index that must wait for the aMAC CTAs covering its items (-1 none)
+    u32 nx, n_ind, n_dep, stride;   // block order, see ladder_block()
+};
+// Block order of the fused launch (1-D grid).  nx = CTAs per job.  First the n_ind independent MSM jobs (job-major) with one
+// aMAC CTA slotted in every `stride` positions, so that at any time only a fraction of the SMs stream aMAC tables; then
+// the n_dep jobs that wait on the aMAC flags.  Returns the job (-1 = aMAC, else position in group_idx) and sets bx.
+__device__ __forceinline__ int ladder_block(const LadderArgs& a, u32 b, u32& bx) {
+    const u32 n_amac = a.amac ? a.nx : 0, head = a.n_ind * a.nx + n_amac;
+    if (b >= head) { u32 m = b - head; bx = m % a.nx; return (int)(a.n_ind + m / a.nx); }
+    u32 m;
+    if (n_amac && b < n_amac * a.stride) {
+        if (b % a.stride == 0) { bx = b / a.stride; return -1; }
+        m = b - (b / a.stride + 1);
+    } else m = b - n_amac;
+    bx = m % a.nx;
+    return (int)(m / a.nx);
 }
 
-__global__ void __launch_bounds__(TPB_MSM, 1) k_msm(Workspace ws, const MsmDesc* msms, const u32* group_idx, u32 scratch_terms) {
+__global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_ladders(Workspace ws, LadderArgs a) {
     extern __shared__ __align__(16) u32 smem[];
-    const MsmDesc& d = msms[group_idx[blockIdx.y]];
-    u32* scratch = smem;                                          // [scratch_terms*8][TPB_MSM]
-    u32* staged = smem + (size_t)scratch_terms * 8 * blockDim.x;  // [<=MSM_STAGE_TABLES][128][24]
+    u32 bx;
+    const int job = ladder_block(a, blockIdx.x, bx);
+    u32 item = bx * blockDim.x + threadIdx.x;
+    bool active = item < ws.count;
+    if (!active) item = ws.count - 1;                              // keep every thread in the barriers of the ladder
+    if (job < 0) {
+        amac_job(ws, *a.amac, item, smem + threadIdx.x, blockDim.x, active);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release(a.flags + bx, a.epoch);
+        return;
+    }
+    const u32 y = (u32)job;
+    const u32 mi = a.group_idx[y];
+    const MsmDesc& d = a.msms[mi];
+    u32* scratch = smem;                                            // [scratch_terms*8][TPB_MSM]
+    u32* staged = smem + (size_t)a.scratch_terms * 8 * blockDim.x;  // [<=MSM_STAGE_TABLES][128][24]
     u32 nstage = d.ncon < MSM_STAGE_TABLES ? d.ncon : MSM_STAGE_TABLES;
     for (u32 k = 0; k < nstage; k++) {
         const uint4* src = reinterpret_cast<const uint4*>(ws.ctabs + (size_t)d.con[k].ctab * CTAB_ENTRIES * 24);
         uint4* dst = reinterpret_cast<uint4*>(staged + (size_t)k * CTAB_ENTRIES * 24);
         for (u32 i = threadIdx.x; i < CTAB_ENTRIES * 24 / 4; i += blockDim.x) dst[i] = src[i];
     }
+    if ((int)mi == a.dep_msm && threadIdx.x == 0) {
+        u32 lo = (bx * blockDim.x) / a.flag_tpb;
+        u32 last_item = bx * blockDim.x + blockDim.x - 1;
+        if (last_item >= ws.count) last_item = ws.count - 1;
+        for (u32 f = lo; f <= last_item / a.flag_tpb; f++)
+            while (ld_acquire(a.flags + f) != a.epoch) __nanosleep(256);
+    }
     __syncthreads();
-    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = item < ws.count;
-    if (!active) item = ws.count - 1;                              // keep every thread in the barriers of the ladder
     CtabResolver ctab_of{staged, ws.ctabs, &d, nstage};
     msm_job(ws, d, item, scratch + threadIdx.x, blockDim.x, ctab_of, active);
 }
 
 // Issuer::issue: the same per-(item, job) ladders with every lookup constant-address (all scalars are secrets)
-__global__ void __launch_bounds__(TPB_MSM, 1) k_msm_ct(Workspace ws, const MsmDesc* msms, const u32* group_idx) {
+__global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_msm_ct(Workspace ws, const MsmDesc* msms, const u32* group_idx) {
     extern __shared__ __align__(16) u32 smem[];
     const MsmDesc& d = msms[group_idx[blockIdx.y]];
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,31 +192,36 @@ static void be_launch_scalar_check(const Workspace& ws, const u16* d_fields, u32
 static void be_launch_points(const Workspace& ws, const PointJob* d_jobs, u32 njobs, be_stream s) {
     k_points<<<grid_for(ws.count, TPB, njobs), TPB, 0, s>>>(ws, d_jobs);
 }
-static void be_launch_amac(const Workspace& ws, const AmacDesc* d, u32 nps, be_stream s) {
-    size_t smem = (size_t)(nps ? nps : 1) * 8 * TPB * 4;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_amac, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    k_amac<<<grid_for(ws.count, TPB, 1), TPB, smem, s>>>(ws, d);
-}
-static void be_launch_msm(const Workspace& ws, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 max_terms, u32 max_con, be_stream s) {
+// One launch for the aMAC ladder (if `amac`) plus the MSMs of one scratch-size group.
+// The last n_dep_jobs entries of d_idx are the MSMs that wait on the aMAC flags.
+static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac_nps, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 n_dep_jobs,
+                             u32 max_terms, u32 max_con, int dep_msm, u32* flags, u32 epoch, u32 flag_tpb, be_stream s) {
     u32 nstage = max_con < (u32)MSM_STAGE_TABLES ? max_con : (u32)MSM_STAGE_TABLES;
+    u32 terms = max_terms > amac_nps ? max_terms : amac_nps;
     // largest CTA (<= TPB_MSM threads) whose digit scratch + staged tables fit in shared memory
     u32 tpb = TPB_MSM;
     size_t smem = 0;
     for (;; tpb /= 2) {
-        smem = (size_t)max_terms * 8 * tpb * 4 + (size_t)nstage * CTAB_ENTRIES * 96;
-        if (smem <= 200 * 1024 || tpb <= 32) break;
+        smem = (size_t)terms * 8 * tpb * 4 + (size_t)nstage * CTAB_ENTRIES * 96;
+        if (smem <= LADDER_SMEM_BUDGET || tpb <= 32) break;
     }
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
-    k_msm<<<grid_for(ws.count, tpb, nidx), tpb, smem, s>>>(ws, d_msms, d_idx, max_terms);
+    if (!attr_set) { cudaFuncSetAttribute(k_ladders, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
+    const u32 nx = (ws.count + tpb - 1) / tpb;
+    const u32 n_dep = n_dep_jobs < nidx ? n_dep_jobs : nidx, n_ind = nidx - n_dep;
+    const u32 head = n_ind * nx + (amac ? nx : 0);
+    u32 stride = amac ? (u32)((uint64_t)head * 7 / 10 / nx) : 1;   // aMAC CTAs spread over the first 70% of the independent work
+    if (stride < 1) stride = 1;
+    LadderArgs a{d_msms, d_idx, terms, amac, flags, epoch, amac ? tpb : flag_tpb, dep_msm, nx, n_ind, n_dep, stride};
+    k_ladders<<<nx * (nidx + (amac ? 1 : 0)), tpb, smem, s>>>(ws, a);
+    return tpb;
 }
 static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 max_terms, be_stream s) {
     u32 tpb = TPB_MSM;
     size_t smem = 0;
     for (;; tpb /= 2) {
         smem = (size_t)max_terms * 8 * tpb * 4;
-        if (smem <= 200 * 1024 || tpb <= 32) break;
+        if (smem <= LADDER_SMEM_BUDGET || tpb <= 32) break;
     }
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_msm_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }

@@ -46,12 +46,13 @@ struct MsmDesc {
 enum : u32 { PJ_COPY = 0, PJ_ADD = 1, PJ_SUB = 2, PJ_UNIFORM = 3 };  // PJ_UNIFORM: from_uniform_bytes(field_a || field_b)
 struct PointJob {
     int16_t field_a, field_b;      // input point fields (field_b = -1 for PJ_COPY)
-    u16 op, pad;
+    u16 op;
+    int16_t atab_slot;             // aMAC-private transposed copy of the ladder table (-1 = none)
     int16_t table_slot, ext_slot;  // -1 = not written
     int16_t comp_slot, compneg_slot;  // compressed encoding of the point / of its negation
 };
 
-struct AmacVar { u16 table_slot, digit_row; };
+struct AmacVar { u16 atab_slot, digit_row; };
 struct AmacPs { u16 ctab, y_row, field_m, pad; };  // (y_i * m_i) * G_m[i] for a revealed scalar attribute
 struct AmacDesc {
     u16 ext_cv, nvar, nps, out_table_slot, out_comp_slot, pad;
@@ -84,6 +85,7 @@ struct Workspace {
     u32 count;
     const u32* fields;   // [n_fields][count][8]
     u32* tables;         // [n_tables][count][8 entries][32]
+    u32* atabs;          // [n_atabs][ceil(count/32)][8 entries][8 quads][32 lanes][4]  aMAC tables, warp-transposed
     u32* ext;            // [n_ext][count][32]
     u32* comp;           // [n_comp][count][8]
     u32* commit;         // [n_msm][count][8]
@@ -136,11 +138,48 @@ AFX_HD pniels load_pniels(const u32* src) { pniels n; n.YpX = load_fe(src); n.Ym
 AFX_HD void store_pniels(u32* dst, const pniels& n) { store_fe(dst, n.YpX); store_fe(dst + 8, n.YmX); store_fe(dst + 16, n.Z); store_fe(dst + 24, n.T2d); }
 AFX_HD aniels load_aniels(const u32* src) { aniels n; n.ypx = load_fe(src); n.ymx = load_fe(src + 8); n.xy2d = load_fe(src + 16); return n; }
 
-struct TableStore { u32* dst; AFX_HD void operator()(int e, const pniels& n) const { store_pniels(dst + 32 * e, n); } };
-AFX_HD void store_table8(u32* dst, const ge& p) { TableStore ts{dst}; ge_table8(p, ts); }
+// The aMAC ladder reads EVERY entry of a table at every step (constant-address scan), so its tables are kept in a
+// warp-transposed layout: the 16-byte quad q of entry e of 32 consecutive items is one contiguous 512-byte run, and a
+// warp's scan is 64 fully coalesced loads instead of 64 loads that each touch 32 different lines.
+AFX_HD void store4(u32* dst, const u32* src) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(dst) = make_uint4(src[0], src[1], src[2], src[3]);
+#else
+    for (int i = 0; i < 4; i++) dst[i] = src[i];
+#endif
+}
+AFX_HD void load4(u32* dst, const u32* src) {
+#if defined(__CUDA_ARCH__)
+    uint4 a = *reinterpret_cast<const uint4*>(src);
+    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+#else
+    for (int i = 0; i < 4; i++) dst[i] = src[i];
+#endif
+}
+constexpr u32 ATAB_QUAD_STRIDE = 128;                       // words between consecutive quads of one item: 32 lanes x 4
+constexpr u32 ATAB_BLOCK_WORDS = 64 * ATAB_QUAD_STRIDE;     // 8 entries x 8 quads
+AFX_HD void store_pniels_t(u32* dst, int e, const pniels& n) {
+    u32* d = dst + (size_t)e * 8 * ATAB_QUAD_STRIDE;
+    store4(d, n.YpX.v); store4(d + ATAB_QUAD_STRIDE, n.YpX.v + 4);
+    store4(d + 2 * ATAB_QUAD_STRIDE, n.YmX.v); store4(d + 3 * ATAB_QUAD_STRIDE, n.YmX.v + 4);
+    store4(d + 4 * ATAB_QUAD_STRIDE, n.Z.v); store4(d + 5 * ATAB_QUAD_STRIDE, n.Z.v + 4);
+    store4(d + 6 * ATAB_QUAD_STRIDE, n.T2d.v); store4(d + 7 * ATAB_QUAD_STRIDE, n.T2d.v + 4);
+}
+struct TableStore {
+    u32* dst; u32* tdst;   // standard / transposed destination, either may be null
+    AFX_HD void operator()(int e, const pniels& n) const {
+        if (dst) store_pniels(dst + 32 * e, n);
+        if (tdst) store_pniels_t(tdst, e, n);
+    }
+};
+AFX_HD void store_table8(u32* dst, const ge& p, u32* tdst = nullptr) { TableStore ts{dst, tdst}; ge_table8(p, ts); }
 
 AFX_HD const u32* field_ptr(const Workspace& ws, u32 f, u32 item) { return ws.fields + ((size_t)f * ws.count + item) * 8; }
 AFX_HD u32* table_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.tables + ((size_t)slot * ws.count + item) * 256; }
+AFX_HD u32* atab_ptr(const Workspace& ws, u32 slot, u32 item) {
+    size_t nblk = ((size_t)ws.count + 31) / 32;
+    return ws.atabs + ((size_t)slot * nblk + item / 32) * ATAB_BLOCK_WORDS + (item % 32) * 4;
+}
 AFX_HD u32* ext_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.ext + ((size_t)slot * ws.count + item) * 32; }
 AFX_HD u32* comp_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.comp + ((size_t)slot * ws.count + item) * 8; }
 AFX_HD u32* commit_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.commit + ((size_t)slot * ws.count + item) * 8; }
@@ -197,9 +236,9 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
     if (j.ext_slot >= 0) store_ge(ext_ptr(ws, (u32)j.ext_slot, item), p);
     if (j.comp_slot >= 0) { ge_compress(w, p); store8(comp_ptr(ws, (u32)j.comp_slot, item), w); }
     if (j.compneg_slot >= 0) { ge_compress(w, ge_neg(p)); store8(comp_ptr(ws, (u32)j.compneg_slot, item), w); }
-    if (j.table_slot >= 0) {
-        store_table8(table_ptr(ws, (u32)j.table_slot, item), p);
-    }
+    if (j.table_slot >= 0 || j.atab_slot >= 0)
+        store_table8(j.table_slot >= 0 ? table_ptr(ws, (u32)j.table_slot, item) : nullptr, p,
+                     j.atab_slot >= 0 ? atab_ptr(ws, (u32)j.atab_slot, item) : nullptr);
 }
 
 // Constant-address table reads: every entry is loaded and the wanted one kept with masks, so neither the branch
@@ -226,6 +265,34 @@ AFX_HD pniels pniels_scan_select(const u32* table, int digit, u32 xneg = 0) {
     for (int i = 0; i < 8; i++) { r.YpX.v[i] = out[i]; r.YmX.v[i] = out[8 + i]; r.Z.v[i] = out[16 + i]; r.T2d.v[i] = out[24 + i]; }
     return pniels_cneg(r, neg);
 }
+// The same scan over a warp-transposed table (tab = atab_ptr(slot, item)).
+AFX_HD pniels pniels_scan_select_t(const u32* tab, int digit, u32 xneg = 0) {
+    u32 neg = ((u32)digit >> 31) ^ xneg;
+    u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
+    u32 out[32];
+    for (int i = 0; i < 32; i++) out[i] = 0;
+    for (u32 e = 1; e <= 8; e++) {
+        u32 m = 0u - (u32)(e == mag);
+        for (int q = 0; q < 8; q++) {
+            u32 w[4]; load4(w, tab + ((size_t)(e - 1) * 8 + q) * ATAB_QUAD_STRIDE);
+            for (int i = 0; i < 4; i++) out[4 * q + i] |= w[i] & m;
+        }
+    }
+    u32 z = (mag == 0);   // digit 0 -> the identity (1, 1, 1, 0)
+    out[0] |= z; out[8] |= z; out[16] |= z;
+    pniels r;
+    for (int i = 0; i < 8; i++) { r.YpX.v[i] = out[i]; r.YmX.v[i] = out[8 + i]; r.Z.v[i] = out[16 + i]; r.T2d.v[i] = out[24 + i]; }
+    return pniels_cneg(r, neg);
+}
+// Pull the next table block of this warp (32 KiB, contiguous) towards L2: each lane touches 8 of its 256 lines.
+AFX_HD void prefetch_atab(const u32* tab_lane0) {
+#if defined(__CUDA_ARCH__)
+    const u32* base = tab_lane0 + (threadIdx.x & 31u) * 8 * 32;   // lane's 8 consecutive 128-byte lines
+    for (int j = 0; j < 8; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 32 * j));
+#else
+    (void)tab_lane0;
+#endif
+}
 AFX_HD aniels aniels_scan_select8(const u32* ctab, int digit, u32 xneg = 0) {
     u32 neg = ((u32)digit >> 31) ^ xneg;
     u32 mag = (u32)((digit ^ (digit >> 31)) - (digit >> 31));
@@ -249,7 +316,7 @@ AFX_HD aniels aniels_scan_select8(const u32* ctab, int digit, u32 xneg = 0) {
 
 // ---- stage: aMAC --------------------------------------------------------------------------------------------
 // scratch: nps * 8 words per item for the recoded (y_i * m_i) scalars; scratch_stride = distance between words
-AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scratch, u32 scratch_stride) {
+AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scratch, u32 scratch_stride, bool active = true) {
     for (u32 k = 0; k < d.nps; k++) {
         sc m = sc_from_words(field_ptr(ws, d.ps[k].field_m, item));
         sc y = sc_from_words(ws.secsc + 8 * d.ps[k].y_row);
@@ -259,11 +326,14 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
     }
     ge acc = ge_identity();
     for (int i = 63; i >= 0; i--) {
+#if defined(__CUDA_ARCH__)
+        AFX_STEP_SYNC();
+#endif
         if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
         for (u32 k = 0; k < d.nvar; k++) {
             int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
-            pniels e = pniels_scan_select(table_ptr(ws, d.var[k].table_slot, item), dig);
-            prefetch_table(table_ptr(ws, d.var[k + 1 < d.nvar ? k + 1 : 0].table_slot, item));   // next lookup, hidden behind this add
+            pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].atab_slot, item), dig);
+            prefetch_atab(atab_ptr(ws, d.var[k + 1 < d.nvar ? k + 1 : 0].atab_slot, item & ~31u));   // next lookup, hidden behind this add
             acc = ge_add_pn(acc, e, true);
         }
         for (u32 k = 0; k < d.nps; k++) {
@@ -273,14 +343,17 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
             acc = ge_madd(acc, e, true);
         }
     }
+    for (u32 k = 0; k < d.nps * 8u; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded y_i * m_i
     // Z = (C_V - W) - acc
     ge cv = load_ge(ext_ptr(ws, d.ext_cv, item));
     ge z = ge_add_pn(cv, pniels_cneg(load_pniels(ws.W_pniels), 1));
     z = ge_sub(z, acc);
     u32 w[8];
     ge_compress(w, z);
-    store8(comp_ptr(ws, d.out_comp_slot, item), w);
-    store_table8(table_ptr(ws, d.out_table_slot, item), z);
+    if (active) {
+        store8(comp_ptr(ws, d.out_comp_slot, item), w);
+        store_table8(table_ptr(ws, d.out_table_slot, item), z);
+    }
 }
 
 // Where constant term k's radix-256 table lives: the first `nstage` are staged in shared memory by the CTA.

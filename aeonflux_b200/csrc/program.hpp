@@ -127,7 +127,7 @@ struct TxBuilder {
 
 // ---- compiled program --------------------------------------------------------------------------------
 struct ShapeProgram {
-    u32 n_fields = 0, n_tables = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
+    u32 n_fields = 0, n_tables = 0, n_atabs = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
     bool is_issue = false;             // Issuer::issue: constant-schedule MSMs, derived scalars, output words instead of verdicts
     std::vector<WideDesc> derived;
     IssueOutDesc issue_out{};
@@ -141,6 +141,7 @@ struct ShapeProgram {
     std::vector<TxHole> holes;
     std::vector<TxIdCheck> ids;
     u32 z_comp_slot = 0;          // where the recomputed Z encoding lands (debug dump)
+    u32 z_msm = 0;                // index of the one MSM that reads Z's ladder table (constraint "Z")
     std::vector<u32> dump_commit; // commit slots that are blinding commitments, in constraint order (debug dump)
 };
 
@@ -214,47 +215,58 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
     for (u32 b : enc_base) for (u32 k = 0; k < 7; k++) P.scalar_fields.push_back((u16)(b + k));
 
     // ---- point jobs
-    u32 ntab = 0, next = 0, ncomp = 0;
-    auto job = [&](int fa, int fb, u32 op, bool table, bool ext, bool comp, bool compneg, int* tslot, int* eslot, int* cslot, int* cnslot) {
-        PointJob j; j.field_a = (int16_t)fa; j.field_b = (int16_t)fb; j.op = (u16)op; j.pad = 0;
-        j.table_slot = table ? (int16_t)ntab++ : -1; j.ext_slot = ext ? (int16_t)next++ : -1;
-        j.comp_slot = comp ? (int16_t)ncomp++ : -1; j.compneg_slot = compneg ? (int16_t)ncomp++ : -1;
-        if (tslot) *tslot = j.table_slot; if (eslot) *eslot = j.ext_slot; if (cslot) *cslot = j.comp_slot; if (cnslot) *cnslot = j.compneg_slot;
+    u32 ntab = 0, natab = 0, next = 0, ncomp = 0;
+    enum : u32 { W_TABLE = 1, W_ATAB = 2, W_EXT = 4, W_COMP = 8, W_COMPNEG = 16 };
+    struct Slots { int table = -1, atab = -1, ext = -1, comp = -1, compneg = -1; };
+    auto job = [&](int fa, int fb, u32 op, u32 want) {
+        Slots o;
+        PointJob j; j.field_a = (int16_t)fa; j.field_b = (int16_t)fb; j.op = (u16)op;
+        j.table_slot = (int16_t)(o.table = (want & W_TABLE) ? (int)ntab++ : -1);
+        j.atab_slot = (int16_t)(o.atab = (want & W_ATAB) ? (int)natab++ : -1);
+        j.ext_slot = (int16_t)(o.ext = (want & W_EXT) ? (int)next++ : -1);
+        j.comp_slot = (int16_t)(o.comp = (want & W_COMP) ? (int)ncomp++ : -1);
+        j.compneg_slot = (int16_t)(o.compneg = (want & W_COMPNEG) ? (int)ncomp++ : -1);
         P.point_jobs.push_back(j);
+        return o;
     };
-    int T_CX0, T_CX1, E_CV;
-    job((int)F_CX0, -1, PJ_COPY, true, false, false, false, &T_CX0, nullptr, nullptr, nullptr);
-    job((int)F_CX1, -1, PJ_COPY, true, false, false, false, &T_CX1, nullptr, nullptr, nullptr);
-    job((int)F_CV, -1, PJ_COPY, false, true, false, false, nullptr, &E_CV, nullptr, nullptr);
-    std::vector<int> T_CY(n, -1), T_X(n, -1);
+    // C_x_0, C_x_1: bases of the aMAC ladder (transposed copy) and of the C_x_1 constraint (standard table)
+    const Slots s_cx0 = job((int)F_CX0, -1, PJ_COPY, W_TABLE | W_ATAB), s_cx1 = job((int)F_CX1, -1, PJ_COPY, W_TABLE | W_ATAB);
+    const int T_CX0 = s_cx0.table, T_CX1 = s_cx1.table;
+    const int E_CV = job((int)F_CV, -1, PJ_COPY, W_EXT).ext;
+    std::vector<int> T_CY(n, -1), A_X(n, -1);   // A_X[i]: aMAC table of X_i (presentation.rs:344-350)
     for (u32 i = 0; i < n; i++) {
-        job((int)(F_CY + i), -1, PJ_COPY, true, false, false, false, &T_CY[i], nullptr, nullptr, nullptr);
-        if (kinds[i] == 2) job((int)(F_CY + i), F_REV[i], PJ_ADD, true, false, false, false, &T_X[i], nullptr, nullptr, nullptr);  // X_i = C_y[i] + M_i (:348)
+        if (kinds[i] == 2) {
+            T_CY[i] = job((int)(F_CY + i), -1, PJ_COPY, W_TABLE).table;
+            A_X[i] = job((int)(F_CY + i), F_REV[i], PJ_ADD, W_ATAB).atab;                        // X_i = C_y[i] + M_i (:348)
+        } else {
+            Slots o = job((int)(F_CY + i), -1, PJ_COPY, (kinds[i] == 3 ? 0u : (u32)W_TABLE) | W_ATAB);   // a hidden point's C_y is only a ladder base
+            T_CY[i] = o.table; A_X[i] = o.atab;
+        }
     }
     struct EncSlots { int T_PK, T_E1, C_NEG_E1, T_CY2, T_CY3, T_CY2P, T_D, C_D; };
     std::vector<EncSlots> es(enc_base.size());
     for (size_t e = 0; e < enc_base.size(); e++) {
         u32 b = enc_base[e];
-        job((int)(b + 7), -1, PJ_COPY, true, false, false, false, &es[e].T_PK, nullptr, nullptr, nullptr);
-        job((int)(b + 8), -1, PJ_COPY, true, false, false, true, &es[e].T_E1, nullptr, nullptr, &es[e].C_NEG_E1);  // E1 and compress(-E1) (encryption.rs:184-185)
-        job((int)(b + 11), -1, PJ_COPY, true, false, false, false, &es[e].T_CY2, nullptr, nullptr, nullptr);
-        job((int)(b + 12), -1, PJ_COPY, true, false, false, false, &es[e].T_CY3, nullptr, nullptr, nullptr);
-        job((int)(b + 13), -1, PJ_COPY, true, false, false, false, &es[e].T_CY2P, nullptr, nullptr, nullptr);
-        job((int)(b + 10), (int)(b + 9), PJ_SUB, true, false, true, false, &es[e].T_D, nullptr, &es[e].C_D, nullptr);  // C_y_1 - E2 (encryption.rs:183)
+        es[e].T_PK = job((int)(b + 7), -1, PJ_COPY, W_TABLE).table;
+        { Slots o = job((int)(b + 8), -1, PJ_COPY, W_TABLE | W_COMPNEG); es[e].T_E1 = o.table; es[e].C_NEG_E1 = o.compneg; }  // E1 and compress(-E1) (encryption.rs:184-185)
+        es[e].T_CY2 = job((int)(b + 11), -1, PJ_COPY, W_TABLE).table;
+        es[e].T_CY3 = job((int)(b + 12), -1, PJ_COPY, W_TABLE).table;
+        es[e].T_CY2P = job((int)(b + 13), -1, PJ_COPY, W_TABLE).table;
+        { Slots o = job((int)(b + 10), (int)(b + 9), PJ_SUB, W_TABLE | W_COMP); es[e].T_D = o.table; es[e].C_D = o.comp; }    // C_y_1 - E2 (encryption.rs:183)
     }
     // ---- aMAC (presentation.rs:342-352)
     P.has_amac = true;
     AmacDesc& A = P.amac; std::memset(&A, 0, sizeof A);
     A.ext_cv = (u16)E_CV;
-    A.var[A.nvar].table_slot = (u16)T_CX0; A.var[A.nvar++].digit_row = (u16)sec_x0();
-    A.var[A.nvar].table_slot = (u16)T_CX1; A.var[A.nvar++].digit_row = (u16)sec_x1();
+    A.var[A.nvar].atab_slot = (u16)s_cx0.atab; A.var[A.nvar++].digit_row = (u16)sec_x0();
+    A.var[A.nvar].atab_slot = (u16)s_cx1.atab; A.var[A.nvar++].digit_row = (u16)sec_x1();
     for (u32 i = 0; i < n; i++) {
-        A.var[A.nvar].table_slot = (u16)(kinds[i] == 2 ? T_X[i] : T_CY[i]); A.var[A.nvar++].digit_row = (u16)sec_y(i);
+        A.var[A.nvar].atab_slot = (u16)A_X[i]; A.var[A.nvar++].digit_row = (u16)sec_y(i);
         if (kinds[i] == 0) { AmacPs& p = A.ps[A.nps++]; p.ctab = (u16)ic.id_Gm(i); p.y_row = (u16)sec_y(i); p.field_m = (u16)F_REV[i]; p.pad = 0; }  // (:346)
     }
     const u32 T_Z = ntab++; const u32 C_Z = ncomp++;
     A.out_table_slot = (u16)T_Z; A.out_comp_slot = (u16)C_Z; P.z_comp_slot = C_Z;
-    P.n_tables = ntab; P.n_ext = next; P.n_comp = ncomp;
+    P.n_tables = ntab; P.n_atabs = natab; P.n_ext = next; P.n_comp = ncomp;
 
     // ---- main proof: constraints (:416-433) and transcript (:355-412)
     const ScalarSrc R_z = sc_field(F_RESP + 0), R_z0 = sc_field(F_RESP + 1), R_t = sc_field(F_RESP + 2), C_main = sc_field(F_CHAL);
@@ -334,7 +346,7 @@ inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const
     P.scalar_fields.push_back((u16)F_T); P.scalar_fields.push_back((u16)F_CHAL);
     for (u32 k = 0; k < n + 5; k++) P.scalar_fields.push_back((u16)(F_RESP + k));
     u32 ntab = 0;
-    auto table_job = [&](u32 field) { PointJob j; j.field_a = (int16_t)field; j.field_b = -1; j.op = PJ_COPY; j.pad = 0; j.table_slot = (int16_t)ntab; j.ext_slot = -1;
+    auto table_job = [&](u32 field) { PointJob j; j.field_a = (int16_t)field; j.field_b = -1; j.op = PJ_COPY; j.atab_slot = -1; j.table_slot = (int16_t)ntab; j.ext_slot = -1;
                                       j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j); return ntab++; };
     const u32 T_U = table_job(F_U), T_V = table_job(F_V);
     std::vector<int> T_M(n, -1);
@@ -403,11 +415,11 @@ inline ShapeProgram compile_issue(const IssuerConsts& ic, u32 n, const uint8_t* 
     // points: U = from_uniform(seed) with its ladder table and encoding; one ladder table per point attribute
     u32 ntab = 0, ncomp = 0;
     u32 T_U, C_U;
-    { PointJob j; j.field_a = (int16_t)F_USEED; j.field_b = (int16_t)(F_USEED + 1); j.op = PJ_UNIFORM; j.pad = 0; j.table_slot = (int16_t)(T_U = ntab++);
+    { PointJob j; j.field_a = (int16_t)F_USEED; j.field_b = (int16_t)(F_USEED + 1); j.op = PJ_UNIFORM; j.atab_slot = -1; j.table_slot = (int16_t)(T_U = ntab++);
       j.ext_slot = -1; j.comp_slot = (int16_t)(C_U = ncomp++); j.compneg_slot = -1; P.point_jobs.push_back(j); }
     std::vector<int> T_M(n, -1);
     for (u32 i = 0; i < n; i++) if (kinds[i] == 2) {
-        PointJob j; j.field_a = (int16_t)(F_ATTR + i); j.field_b = -1; j.op = PJ_COPY; j.pad = 0; j.table_slot = (int16_t)(T_M[i] = (int)ntab++);
+        PointJob j; j.field_a = (int16_t)(F_ATTR + i); j.field_b = -1; j.op = PJ_COPY; j.atab_slot = -1; j.table_slot = (int16_t)(T_M[i] = (int)ntab++);
         j.ext_slot = -1; j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j);
     }
     P.n_tables = ntab; P.n_ext = 0; P.n_comp = ncomp;

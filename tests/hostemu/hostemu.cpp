@@ -35,17 +35,16 @@ static void be_launch_scalar_check(const Workspace& ws, const u16* f, u32 nf, be
 static void be_launch_points(const Workspace& ws, const PointJob* jobs, u32 nj, be_stream) {
     for (u32 k = 0; k < nj; k++) for (u32 i = 0; i < ws.count; i++) points_job(ws, jobs[k], i);
 }
-static void be_launch_amac(const Workspace& ws, const AmacDesc* d, u32 nps, be_stream) {
-    std::vector<u32> scratch((size_t)(nps ? nps : 1) * 8);
-    for (u32 i = 0; i < ws.count; i++) amac_job(ws, *d, i, scratch.data(), 1);
-}
-static void be_launch_msm(const Workspace& ws, const MsmDesc* msms, const u32* idx, u32 nidx, u32 max_terms, u32, be_stream) {
-    std::vector<u32> scratch((size_t)max_terms * 8);
+static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 nps, const MsmDesc* msms, const u32* idx, u32 nidx, u32, u32 max_terms, u32,
+                             int, u32*, u32, u32, be_stream) {
+    std::vector<u32> scratch((size_t)(max_terms > nps ? max_terms : nps) * 8 + 8);
+    if (amac) for (u32 i = 0; i < ws.count; i++) amac_job(ws, *amac, i, scratch.data(), 1);
     for (u32 k = 0; k < nidx; k++) {
         const MsmDesc& d = msms[idx[k]];
         CtabResolver r{nullptr, ws.ctabs, &d, 0};
         for (u32 i = 0; i < ws.count; i++) msm_job(ws, d, i, scratch.data(), 1, r);
     }
+    return 1;
 }
 static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* msms, const u32* idx, u32 nidx, u32 max_terms, be_stream) {
     std::vector<u32> scratch((size_t)max_terms * 8);
