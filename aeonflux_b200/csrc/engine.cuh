@@ -433,7 +433,7 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
         for (u32 k = 0; k < d.nvar; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
-            pniels e = pniels_scan_select(table_ptr(ws, d.var[k].table_slot, item), dig, d.var[k].neg);
+            pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].table_slot, item), dig, d.var[k].neg);
             acc = ge_add_pn(acc, e, true);
         }
         for (u32 k = 0; k < d.ncon; k++) {

@@ -412,17 +412,19 @@ inline ShapeProgram compile_issue(const IssuerConsts& ic, u32 n, const uint8_t* 
     auto B_y = [&](u32 i) { return D_B(4 + i); };
     const u32 S_w = sref_secret(2 + n), S_wp = sref_secret(3 + n), S_x0 = sref_secret(sec_x0()), S_x1 = sref_secret(sec_x1());
     (void)S_w; (void)S_wp;
-    // points: U = from_uniform(seed) with its ladder table and encoding; one ladder table per point attribute
+    // points: U = from_uniform(seed) with its ladder table and encoding; one ladder table per point attribute.  Every lookup
+    // on this path is a constant-address scan, so the tables only exist in the warp-transposed layout (table_slot of a
+    // variable term = transposed slot).
     u32 ntab = 0, ncomp = 0;
     u32 T_U, C_U;
-    { PointJob j; j.field_a = (int16_t)F_USEED; j.field_b = (int16_t)(F_USEED + 1); j.op = PJ_UNIFORM; j.atab_slot = -1; j.table_slot = (int16_t)(T_U = ntab++);
+    { PointJob j; j.field_a = (int16_t)F_USEED; j.field_b = (int16_t)(F_USEED + 1); j.op = PJ_UNIFORM; j.table_slot = -1; j.atab_slot = (int16_t)(T_U = ntab++);
       j.ext_slot = -1; j.comp_slot = (int16_t)(C_U = ncomp++); j.compneg_slot = -1; P.point_jobs.push_back(j); }
     std::vector<int> T_M(n, -1);
     for (u32 i = 0; i < n; i++) if (kinds[i] == 2) {
-        PointJob j; j.field_a = (int16_t)(F_ATTR + i); j.field_b = -1; j.op = PJ_COPY; j.atab_slot = -1; j.table_slot = (int16_t)(T_M[i] = (int)ntab++);
+        PointJob j; j.field_a = (int16_t)(F_ATTR + i); j.field_b = -1; j.op = PJ_COPY; j.table_slot = -1; j.atab_slot = (int16_t)(T_M[i] = (int)ntab++);
         j.ext_slot = -1; j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j);
     }
-    P.n_tables = ntab; P.n_ext = 0; P.n_comp = ncomp;
+    P.n_tables = 0; P.n_atabs = ntab; P.n_ext = 0; P.n_comp = ncomp;
     u32 slot = 0;
     auto D = [](u32 d) { return sc_field(sref_derived(d)); };
     // M_i = m_i * G_m[i] (amacs.rs:234-235), tU = t * U (issuance.rs:91)

@@ -312,12 +312,18 @@ def main():
         pass
     sm_max = clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     imad_peak = 148 * 64 * sm_max * 1e6                       # IMAD issue slots/s at max clock (measured 18.52e12 by tools/microbench)
-    msm_ms = stage_sum["msm"] / args.steps
-    msm_imad = 2 * wm["msm"] * B                              # algorithmic IMAD slots per launch group of the dominant kernel (k_msm)
+    # dominant kernel: k_ladders = the aMAC ladder + every constraint MSM of the batch in one launch (stages "amac" + "msm")
+    msm_ms = (stage_sum["msm"] + stage_sum["amac"]) / args.steps
+    msm_imad = 2 * (wm["msm"] + wm["amac"]) * B               # algorithmic IMAD slots per launch of k_ladders
     achieved = msm_imad / (msm_ms * 1e-3)
+    traffic = None
+    try:   # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/), not a live number
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("k_ladders")
+    except (OSError, ValueError):
+        pass
     hbm_bytes = B * (WORDS * 32 + 1)
-    roofline = {"bound": "imad", "kernel": "k_msm", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": achieved / imad_peak,
-                "traffic": None, "peak_source": "148 SMs x 64 IMAD/clk x sm_max_mhz; tools/microbench measured 18.52 T IMAD/s and 9.12 T IMAD.WIDE/s (profiles/r01_microbench_imad.json)",
+    roofline = {"bound": "imad", "kernel": "k_ladders", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": achieved / imad_peak,
+                "traffic": traffic, "peak_source": "148 SMs x 64 IMAD/clk x sm_max_mhz; tools/microbench measured 18.52 T IMAD/s and 9.12 T IMAD.WIDE/s (profiles/r01_microbench_imad.json)",
                 "algorithmic_imad_per_item": {k: 2 * v for k, v in wm.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_sum.items()},
                 "pipeline_frac_of_imad_peak": (B * args.steps * 2 * wm["total"] / (dev_ms * 1e-3)) / imad_peak,

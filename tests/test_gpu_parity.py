@@ -211,3 +211,34 @@ def test_issue_full_size_round_trip(readme4):
     expect = np.zeros(count, np.uint8)
     expect[bad] = 1
     assert (v == expect).all()
+
+
+def test_mixed_stream_reduced_config5(coracle):
+    """BASELINE configs[4] at reduced size through the sharding layer (world 1): README-4 and S16 presentations interleaved
+    item by item, 1 % corrupted; verdicts come back in stream order and match the corrupted set and the oracle."""
+    from aeonflux_b200 import Issuer
+    from aeonflux_b200.shard import ShardedIssuer
+    iss, orc, base = {}, {}, {}
+    for n, rk, hide, cfg in ((4, b"SSPE", [0, 3], b"mix4"), (16, b"SSSSSSPP" + b"E" * 8, [0, 1] + list(range(8, 16)), b"mix16")):
+        sp, ip, sk = coracle.make_issuer(n)
+        orc[n] = coracle.Issuer(sp, ip, sk)
+        iss[n] = Issuer(sp, ip, sk, device=0, max_batch=2048)
+        kinds, pres, _ = orc[n].synth(rk, hide, cfg, 0, 64, want_issuances=False)
+        base[n] = (kinds, pres)
+    rng = np.random.default_rng(9)
+    total = 6000
+    kl, items, expect = [], [], np.zeros(total, np.uint8)
+    for i in range(total):
+        n = 4 if rng.random() < 0.5 else 16
+        kinds, pres = base[n]
+        w = pres[rng.integers(0, len(pres))].copy()
+        if rng.random() < 0.01:
+            w[rng.integers(0, w.shape[0]), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+            expect[i] = 1
+        kl.append(kinds); items.append(w)
+    v = ShardedIssuer(iss[4]).verify_mixed(kl, items, issuers=iss)
+    assert (v == expect).all() and expect.sum() > 20
+    for n in (4, 16):
+        sel = [i for i in range(total) if len(kl[i]) == n][:200]
+        ov, _ = orc[n].verify_presentations(base[n][0], np.ascontiguousarray(np.stack([items[i] for i in sel])))
+        assert (ov == v[sel]).all()

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""BASELINE configs[4]: streamed verification of N mixed presentations (50 % README-4, 50 % S16, 1 % corrupted), bucketed by
+shape into chunks of 65,536 and sharded over the ranks of the process group (contiguous slices, verdict bitmap gathered).
+
+    python tools/stream_config5.py [--items 4194304] [--chunk 65536]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tools/stream_config5.py ...
+
+Inputs are tiled from the committed bench fixtures (every item is independent, so tiling changes neither work nor traffic);
+corruption = one flipped bit in a random word, which every verdict must catch (every word of a presentation is bound by a
+transcript).  A random sample of each chunk is cross-checked against the CPU oracle.  Prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+K4 = bytes([1, 0, 2, 3])
+K16 = bytes([1, 1, 0, 0, 0, 0, 2, 2] + [3] * 8)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--items", type=int, default=1 << 22)
+    ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--oracle-sample", type=int, default=32)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from aeonflux_b200.shard import ShardedIssuer, slice_bounds
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    b4 = open(os.path.join(ROOT, "bench_data", "issuer4.bin"), "rb").read()
+    b16 = open(os.path.join(ROOT, "bench_data", "issuer16.bin"), "rb").read()
+    p4 = np.fromfile(os.path.join(ROOT, "bench_data", "readme4_1024.bin"), np.uint8).reshape(-1, 28, 32)
+    p16 = np.fromfile(os.path.join(ROOT, "bench_data", "s16_256.bin"), np.uint8).reshape(-1, 143, 32)
+    per_rank = -(-args.chunk // world)
+    iss = {4: Issuer(b4[:548], b4[548:612], b4[612:], device=local, max_batch=per_rank),
+           16: Issuer(b16[:1316], b16[1316:1380], b16[1380:], device=local, max_batch=per_rank)}
+    sh = {n: ShardedIssuer(i) for n, i in iss.items()}
+    orc = None
+    if rank == 0 and args.oracle_sample:
+        from oracle import coracle as C
+        orc = {4: C.Issuer(b4[:548], b4[548:612], b4[612:]), 16: C.Issuer(b16[:1316], b16[1316:1380], b16[1380:])}
+    rng = np.random.default_rng(5)          # same stream on every rank: each rank builds the chunk and takes its slice
+    n_chunks = args.items // args.chunk
+    done, rejected, expected_rejected, mism, oracle_checked, busy = 0, 0, 0, 0, 0, 0.0
+    t_start = time.perf_counter()
+    for c in range(n_chunks):
+        n, kinds, base = (4, K4, p4) if c % 2 == 0 else (16, K16, p16)     # chunks alternate between the two shape buckets
+        start = int(rng.integers(0, len(base)))
+        idx = (start + np.arange(args.chunk)) % len(base)
+        items = base[idx]                                                    # [chunk][W][32]
+        bad = rng.choice(args.chunk, args.chunk // 100, replace=False)
+        items[bad, rng.integers(0, items.shape[1], len(bad)), rng.integers(0, 31, len(bad))] ^= (1 << rng.integers(0, 8, len(bad))).astype(np.uint8)
+        expect = np.zeros(args.chunk, np.uint8); expect[bad] = 1
+        batch = PresentationBatch.from_items(kinds, items)
+        t0 = time.perf_counter()
+        v = sh[n].verify_batch(batch)
+        busy += time.perf_counter() - t0
+        mism += int((v != expect).sum())
+        rejected += int(v.sum()); expected_rejected += len(bad); done += args.chunk
+        if orc is not None:
+            sample = np.concatenate([bad[:args.oracle_sample // 2], rng.choice(args.chunk, args.oracle_sample // 2, replace=False)])
+            ov, _ = orc[n].verify_presentations(kinds, np.ascontiguousarray(items[sample]))
+            mism += int((ov != v[sample]).sum()); oracle_checked += len(sample)
+    wall = time.perf_counter() - t_start
+    if rank == 0:
+        print(json.dumps({"workload": "streamed verification of %d mixed presentations (README-4 / S16 chunks of %d alternating, 1%% corrupted)" % (done, args.chunk),
+                          "n_gpus": world, "items": done, "verify_seconds": busy, "wall_seconds_incl_input_synthesis": wall,
+                          "presentations_per_s": done / busy, "rejected": rejected, "expected_rejected": expected_rejected,
+                          "mismatches": mism, "oracle_cross_checked": oracle_checked}))
+    if world > 1:
+        dist.destroy_process_group()
+    if mism:
+        raise SystemExit("verdict mismatches: %d" % mism)
+
+
+if __name__ == "__main__":
+    main()
