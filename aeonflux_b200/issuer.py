@@ -29,9 +29,14 @@ class PresentationBatch:
 
     def __init__(self, kinds, fields):
         self.kinds = bytes(kinds)
-        self.fields = np.ascontiguousarray(fields, dtype=np.uint8)
-        if self.fields.ndim != 3 or self.fields.shape[2] != 32:
+        fields = np.asarray(fields, dtype=np.uint8)
+        if fields.ndim != 3 or fields.shape[2] != 32:
             raise ValueError("fields must be [n_fields][count][32] bytes")
+        # each field must be one contiguous [count][32] run (that is all the C ABI needs); an item slice of a batch
+        # (fields[:, lo:hi]) already is, so sharding a batch copies nothing
+        if not all(fields[f].flags.c_contiguous for f in range(fields.shape[0])):
+            fields = np.ascontiguousarray(fields)
+        self.fields = fields
 
     @property
     def count(self):

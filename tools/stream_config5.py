@@ -50,6 +50,7 @@ def main():
         from oracle import coracle as C
         orc = {4: C.Issuer(b4[:548], b4[548:612], b4[612:]), 16: C.Issuer(b16[:1316], b16[1316:1380], b16[1380:])}
     rng = np.random.default_rng(5)          # same stream on every rank: each rank builds the chunk and takes its slice
+    srng = np.random.default_rng(6)         # rank 0's oracle sampling draws must not disturb the shared stream
     n_chunks = args.items // args.chunk
     done, rejected, expected_rejected, mism, oracle_checked, busy = 0, 0, 0, 0, 0, 0.0
     t_start = time.perf_counter()
@@ -62,13 +63,15 @@ def main():
         items[bad, rng.integers(0, items.shape[1], len(bad)), rng.integers(0, 31, len(bad))] ^= (1 << rng.integers(0, 8, len(bad))).astype(np.uint8)
         expect = np.zeros(args.chunk, np.uint8); expect[bad] = 1
         batch = PresentationBatch.from_items(kinds, items)
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         v = sh[n].verify_batch(batch)
         busy += time.perf_counter() - t0
         mism += int((v != expect).sum())
         rejected += int(v.sum()); expected_rejected += len(bad); done += args.chunk
         if orc is not None:
-            sample = np.concatenate([bad[:args.oracle_sample // 2], rng.choice(args.chunk, args.oracle_sample // 2, replace=False)])
+            sample = np.concatenate([bad[:args.oracle_sample // 2], srng.choice(args.chunk, args.oracle_sample // 2, replace=False)])
             ov, _ = orc[n].verify_presentations(kinds, np.ascontiguousarray(items[sample]))
             mism += int((ov != v[sample]).sum()); oracle_checked += len(sample)
     wall = time.perf_counter() - t_start
