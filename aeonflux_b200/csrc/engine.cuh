@@ -329,18 +329,18 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
 #if defined(__CUDA_ARCH__)
         AFX_STEP_SYNC();
 #endif
-        if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+        if (i != 63) ge_dbl4(acc);
         for (u32 k = 0; k < d.nvar; k++) {
             int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
             pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].atab_slot, item), dig);
             prefetch_atab(atab_ptr(ws, d.var[k + 1 < d.nvar ? k + 1 : 0].atab_slot, item & ~31u));   // next lookup, hidden behind this add
-            acc = ge_add_pn(acc, e, true);
+            GE_LADDER_ADD(acc, e);
         }
         for (u32 k = 0; k < d.nps; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.ps[k].ctab * CTAB_ENTRIES * 24, dig);
-            acc = ge_madd(acc, e, true);
+            GE_LADDER_MADD(acc, e);
         }
     }
     for (u32 k = 0; k < d.nps * 8u; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded y_i * m_i
@@ -384,7 +384,7 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
 #if defined(__CUDA_ARCH__)
         AFX_STEP_SYNC();
 #endif
-        if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+        if (i != 63) ge_dbl4(acc);
         for (u32 k = 0; k < d.nvar; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
@@ -392,7 +392,8 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                 u32 neg = ((u32)dig >> 31) ^ d.var[k].neg;
                 u32 mag = (u32)(dig < 0 ? -dig : dig);
                 pniels e = load_pniels(table_ptr(ws, d.var[k].table_slot, item) + 32 * (mag - 1));
-                acc = ge_add_pn(acc, pniels_cneg(e, neg), true);
+                e = pniels_cneg(e, neg);
+                GE_LADDER_ADD(acc, e);
             }
         }
         if ((i & 1) == 0) {
@@ -403,7 +404,8 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                     u32 neg = ((u32)dig >> 31) ^ d.con[k].neg;
                     u32 mag = (u32)(dig < 0 ? -dig : dig);
                     aniels e = load_aniels(ctab_of(k) + 24 * (mag - 1));
-                    acc = ge_madd(acc, aniels_cneg(e, neg), true);
+                    e = aniels_cneg(e, neg);
+                    GE_LADDER_MADD(acc, e);
                 }
             }
         }
@@ -429,18 +431,18 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
 #if defined(__CUDA_ARCH__)
         AFX_STEP_SYNC();
 #endif
-        if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+        if (i != 63) ge_dbl4(acc);
         for (u32 k = 0; k < d.nvar; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].table_slot, item), dig, d.var[k].neg);
-            acc = ge_add_pn(acc, e, true);
+            GE_LADDER_ADD(acc, e);
         }
         for (u32 k = 0; k < d.ncon; k++) {
             u32 word = scratch[((d.nvar + k) * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.con[k].ctab * CTAB_ENTRIES * 24, dig, d.con[k].neg);
-            acc = ge_madd(acc, e, true);
+            GE_LADDER_MADD(acc, e);
         }
     }
     for (u32 k = 0; k < ((u32)d.nvar + d.ncon) * 8; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded secrets
