@@ -184,6 +184,11 @@ static void be_event_destroy(be_event e) { cudaEventDestroy(e); }
 static void be_event_record(be_event e, be_stream s) { cudaEventRecord(e, s); }
 static int be_event_sync(be_event e) { return cudaEventSynchronize(e) != cudaSuccess; }
 static float be_event_elapsed(be_event a, be_event b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+static int be_stream_create(be_stream* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess; }
+static void be_stream_destroy(be_stream s) { cudaStreamDestroy(s); }
+static void be_stream_wait(be_stream s, be_event e) { cudaStreamWaitEvent(s, e, 0); }
+static int be_host_alloc(void** p, size_t n) { return cudaHostAlloc(p, n, cudaHostAllocDefault) != cudaSuccess; }
+static void be_host_free(void* p) { cudaFreeHost(p); }
 static dim3 grid_for(u32 count, u32 tpb, u32 y) { return dim3((count + tpb - 1) / tpb, y, 1); }
 
 static void be_launch_scalar_check(const Workspace& ws, const u16* d_fields, u32 nf, be_stream s) {

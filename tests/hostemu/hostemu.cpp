@@ -28,6 +28,11 @@ static void be_event_destroy(be_event) {}
 static void be_event_record(be_event, be_stream) {}
 static int be_event_sync(be_event) { return 0; }
 static float be_event_elapsed(be_event, be_event) { return 0.f; }
+static int be_stream_create(be_stream* s) { *s = nullptr; return 0; }
+static void be_stream_destroy(be_stream) {}
+static void be_stream_wait(be_stream, be_event) {}
+static int be_host_alloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 16); return *p == nullptr; }
+static void be_host_free(void* p) { std::free(p); }
 
 static void be_launch_scalar_check(const Workspace& ws, const u16* f, u32 nf, be_stream) {
     for (u32 k = 0; k < nf; k++) for (u32 i = 0; i < ws.count; i++) scalar_check_job(ws, f[k], i);

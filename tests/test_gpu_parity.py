@@ -242,3 +242,24 @@ def test_mixed_stream_reduced_config5(coracle):
         sel = [i for i in range(total) if len(kl[i]) == n][:200]
         ov, _ = orc[n].verify_presentations(base[n][0], np.ascontiguousarray(np.stack([items[i] for i in sel])))
         assert (ov == v[sel]).all()
+
+
+def test_multi_chunk_host_call_is_pipelined_and_exact(readme4):
+    """A host call longer than max_batch takes the double-buffered copy/execute path: same verdicts as the oracle, in order,
+    for a ragged number of chunks."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    orc, _, (sp, ip, sk) = readme4
+    count = 5 * 1024 + 333
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"pipelined", 0, count)
+    rng = np.random.default_rng(31)
+    bad = rng.choice(count, 97, replace=False)
+    for i in bad:
+        pres[i, rng.integers(0, 28), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+    iss = Issuer(sp, ip, sk, device=0, max_batch=1024)
+    v = iss.verify_batch(PresentationBatch.from_items(kinds, pres))
+    ov, _ = orc.verify_presentations(kinds, pres)
+    assert (v == ov).all() and set(np.where(v)[0]) == set(bad)
+    issu[77, 5, 3] ^= 4
+    vi = iss.verify_issuance_batch(PresentationBatch.from_items(bytes([0, 0, 2, 2]), issu))
+    ovi, _ = orc.verify_issuances(bytes([0, 0, 2, 2]), issu)
+    assert (vi == ovi).all() and vi.sum() == 1

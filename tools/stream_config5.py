@@ -26,7 +26,9 @@ K16 = bytes([1, 1, 0, 0, 0, 0, 2, 2] + [3] * 8)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--items", type=int, default=1 << 22)
-    ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--chunk", type=int, default=65536, help="items per host call (one shape bucket)")
+    ap.add_argument("--max-batch", type=int, default=0, help="items per device pass and per GPU (default: chunk / world); a host call "
+                    "longer than this is pipelined inside the library (H2D of pass i+1 under the kernels of pass i)")
     ap.add_argument("--oracle-sample", type=int, default=32)
     args = ap.parse_args()
     import torch
@@ -41,7 +43,7 @@ def main():
     b16 = open(os.path.join(ROOT, "bench_data", "issuer16.bin"), "rb").read()
     p4 = np.fromfile(os.path.join(ROOT, "bench_data", "readme4_1024.bin"), np.uint8).reshape(-1, 28, 32)
     p16 = np.fromfile(os.path.join(ROOT, "bench_data", "s16_256.bin"), np.uint8).reshape(-1, 143, 32)
-    per_rank = -(-args.chunk // world)
+    per_rank = args.max_batch or -(-args.chunk // world)
     iss = {4: Issuer(b4[:548], b4[548:612], b4[612:], device=local, max_batch=per_rank),
            16: Issuer(b16[:1316], b16[1316:1380], b16[1380:], device=local, max_batch=per_rank)}
     sh = {n: ShardedIssuer(i) for n, i in iss.items()}
