@@ -51,32 +51,47 @@ def work_model(kinds):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  Started before the warm-up (nvidia-smi needs a moment to
+    come up, longer on an 8-GPU box) and polled every 25 ms; rows are time-stamped on arrival and summary() only uses those
+    that arrived inside the marked timed windows."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
-    def __enter__(self):
+    def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: [self.rows.append(line) for line in self.proc.stdout], daemon=True)
+            self.t = threading.Thread(target=lambda: [self.rows.append((time.time(), line)) for line in self.proc.stdout], daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
         return self
 
-    def __exit__(self, *a):
+    def window(self):
+        sampler = self
+
+        class _W:
+            def __enter__(self):
+                self.t0 = time.time()
+
+            def __exit__(self, *a):
+                sampler.windows.append((self.t0, time.time()))
+        return _W()
+
+    def stop(self):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for line in self.rows:
+        for ts, line in self.rows:
+            if not any(a <= ts <= b + 0.03 for a, b in self.windows):
+                continue
             p = [x.strip() for x in line.split(",")]
             if len(p) < 7:
                 continue
@@ -88,8 +103,9 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "samples": 0, "rows_total": len(self.rows)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "windows": "device-resident and end-to-end timed regions"}
 
 
 def load_fixture(batch):
@@ -255,13 +271,14 @@ def main():
         return e0, e1
 
     # ---- kernel-only: inputs resident in HBM --------------------------------------------------------------------
+    clocks = ClockSampler(local).start()
     issuer.set_stage_timing(True)
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     launches0 = issuer.launch_count
     stage_sum = {k: 0.0 for k in Issuer.STAGES}
-    with ClockSampler(local) as clocks:
+    with clocks.window():
         evs = []
         for _ in range(args.steps):
             evs.append(step_device())
@@ -280,12 +297,14 @@ def main():
         issuer.verify_batch(batch)
     barrier()
     e2e_s = 0.0
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        v = issuer.verify_batch(batch)
-        e2e_s += time.perf_counter() - t0
-        assert not v.any()
+    with clocks.window():
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            v = issuer.verify_batch(batch)
+            e2e_s += time.perf_counter() - t0
+            assert not v.any()
     barrier()
+    clocks.stop()
 
     secondary = None
     if world == 1 and not args.no_secondary:
