@@ -83,7 +83,9 @@ struct IssueOutDesc {
 // All arrays are slot-major then item-major; an item's 32-byte word is 8 consecutive u32 (two 128-bit loads).
 struct Workspace {
     u32 count;
-    const u32* fields;   // [n_fields][count][8]
+    const u32* fields;   // struct-of-arrays [n_fields][count][8] (fs_field = count, fs_item = 1) or item-major "wire"
+                         // [count][n_fields][8] (fs_field = 1, fs_item = n_fields); strides in 32-byte words
+    u32 fs_field, fs_item;
     u32* tables;         // [n_tables][count][8 entries][32]
     u32* atabs;          // [n_atabs][ceil(count/32)][8 entries][8 quads][32 lanes][4]  aMAC tables, warp-transposed
     u32* ext;            // [n_ext][count][32]
@@ -174,7 +176,7 @@ struct TableStore {
 };
 AFX_HD void store_table8(u32* dst, const ge& p, u32* tdst = nullptr) { TableStore ts{dst, tdst}; ge_table8(p, ts); }
 
-AFX_HD const u32* field_ptr(const Workspace& ws, u32 f, u32 item) { return ws.fields + ((size_t)f * ws.count + item) * 8; }
+AFX_HD const u32* field_ptr(const Workspace& ws, u32 f, u32 item) { return ws.fields + ((size_t)f * ws.fs_field + (size_t)item * ws.fs_item) * 8; }
 AFX_HD u32* table_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.tables + ((size_t)slot * ws.count + item) * 256; }
 AFX_HD u32* atab_ptr(const Workspace& ws, u32 slot, u32 item) {
     size_t nblk = ((size_t)ws.count + 31) / 32;

@@ -147,6 +147,18 @@ class Issuer:
         """Batch Issuer::verify (issuer.rs:141-147): verdict 0 = Ok(()), 1 = Err(VerificationFailure)."""
         return self._run(self._b.L.afx_verify_presentations, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
 
+    def verify_wire(self, kinds, items, issuance=False):
+        """Batch Issuer::verify (or CredentialIssuance::verify) over item-major wire bytes: items = uint8 [count][n_fields][32],
+        the concatenation of each item's words.  One H2D copy; no per-field scatter on the host."""
+        items = np.ascontiguousarray(items, dtype=np.uint8)
+        nf = (2 * len(kinds) + 9) if issuance else self.num_fields(kinds)
+        if items.ndim != 3 or items.shape[1:] != (nf, 32):
+            raise ValueError("items must be [count][%d][32] bytes for this shape" % nf)
+        verdicts = np.zeros(items.shape[0], np.uint8)
+        fn = self._b.L.afx_verify_issuances_wire if issuance else self._b.L.afx_verify_presentations_wire
+        self._b.check(fn(self._h, len(kinds), bytes(kinds), items.shape[0], items.ctypes.data, verdicts.ctypes.data))
+        return verdicts
+
     def verify_issuance_batch(self, batch: IssuanceBatch, debug=False):
         """Batch CredentialIssuance::verify (issuer.rs:48-57)."""
         return self._run(self._b.L.afx_verify_issuances, batch, 3, 1, debug)

@@ -97,6 +97,17 @@ typedef struct {
 /* Batch CredentialIssuance::verify (src/issuer.rs:48-57 -> src/nizk/issuance.rs:132-218).  Needs no secret key. */
 int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
 
+/* Item-major ("wire") variants.  The reference defines no serialization for a presentation or an issuance
+ * (src/nizk/presentation.rs:117 "XXX"); the natural one is the concatenation of the item's 32-byte words in
+ * the field order documented above, and a batch is the concatenation of its items:
+ *     items = [count][n_fields][32] contiguous bytes.
+ * These take such a blob as received -- one host-to-device copy, no scatter into per-field arrays; the kernels read the
+ * item-major layout directly (32 contiguous bytes per word either way).  Verdicts and chunking/pipelining as above. */
+int afx_verify_presentations_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                                  uint8_t* verdicts);
+int afx_verify_issuances_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                              uint8_t* verdicts);
+
 /* Same as afx_verify_issuances with the batch resident on the device ([2*n_attrs + 9][count][32] contiguous). */
 int afx_verify_issuances_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev,
                                 void* verdicts_dev, void* stream);

@@ -263,3 +263,8 @@ def test_multi_chunk_host_call_is_pipelined_and_exact(readme4):
     vi = iss.verify_issuance_batch(PresentationBatch.from_items(bytes([0, 0, 2, 2]), issu))
     ovi, _ = orc.verify_issuances(bytes([0, 0, 2, 2]), issu)
     assert (vi == ovi).all() and vi.sum() == 1
+    # the same batches as item-major wire blobs (pipelined, 6 chunks) and in one pass
+    assert (iss.verify_wire(kinds, pres) == ov).all()
+    assert (iss.verify_wire(bytes([0, 0, 2, 2]), issu, issuance=True) == ovi).all()
+    big = Issuer(sp, ip, sk, device=0, max_batch=8192)
+    assert (big.verify_wire(kinds, pres) == ov).all()

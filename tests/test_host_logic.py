@@ -92,6 +92,10 @@ def test_stage_logic_matches_oracle_on_golden_shapes(emu, coracle, name):
     assert dbgi["commitments"][:, 0].tobytes().hex() == "".join(e["issuance_commitments"])
     user = Issuer(sp, ip, None, max_batch=8, _binding=emu)     # user-side context: no secret key
     assert (user.verify_issuance_batch(PresentationBatch.from_items(ik, issu)) == ovi).all()
+    # item-major wire blobs (one copy, kernels read the item-major layout): same verdicts; 5 items over max_batch 3 = pipelined chunks
+    assert (iss.verify_wire(kinds, pres) == ov).all()
+    assert (user.verify_wire(ik, issu, issuance=True) == ovi).all()
+    assert len(iss.verify_wire(kinds, pres[:0])) == 0
 
 
 @pytest.mark.parametrize("name", GOLDEN_SHAPES)
