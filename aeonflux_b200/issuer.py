@@ -96,6 +96,13 @@ class Issuer:
         self._b.check(rc)
         self._h = h
 
+    @classmethod
+    def from_bytes(cls, blob: bytes, **kw):
+        """Issuer::from_bytes (issuer.rs:152-159): sysparams || C_W || I || secret key."""
+        from .wire import issuer_from_bytes
+        sp, ip, sk = issuer_from_bytes(blob)
+        return cls(sp, ip, sk, **kw)
+
     def close(self):
         if getattr(self, "_h", None):
             self._b.L.afx_ctx_destroy(self._h)

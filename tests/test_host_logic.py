@@ -185,3 +185,39 @@ def test_corruption_classes_and_edges(emu, coracle):
         Issuer(bytes(bad), ip, sk, _binding=emu)
     with pytest.raises(AfxError):
         Issuer(sp[:-1], ip, sk, _binding=emu)
+
+
+def test_key_material_layouts_round_trip(emu, coracle):
+    """aeonflux_b200.wire: the reference's to_bytes layouts, Issuer::{to,from}_bytes, and the SecretKey::from_bytes y-loop fix."""
+    from aeonflux_b200 import Issuer, PresentationBatch, wire
+    for name in ("readme4", "scalar1", "s16"):
+        g = load_golden(name)
+        sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+        n = g["n"]
+        assert len(sp) == wire.system_parameters_size(n) and len(sk) == wire.secret_key_size(n)
+        P = wire.split_system_parameters(sp)
+        assert P["n"] == n and len(P["G_y"]) == max(n, 3) and len(P["G_m"]) == n
+        assert P["G"].hex() == "e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76"     # the ristretto basepoint
+        assert wire.join_system_parameters(P) == sp
+        K = wire.split_secret_key(sk)
+        assert wire.join_secret_key(K) == sk
+        if n > 1:
+            assert len(set(K["y"])) == n            # every y_i read from its own bytes (amacs.rs:148-150 would repeat y_0)
+        assert wire.issuer_parameters_from_bytes(wire.issuer_parameters_to_bytes(ip[:32], ip[32:])) == (ip[:32], ip[32:])
+        blob = wire.issuer_to_bytes(sp, ip, sk)
+        assert wire.issuer_from_bytes(blob) == (sp, ip, sk)
+    # an Issuer restored from Issuer::to_bytes bytes verifies like the original
+    g = load_golden("readme4")
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    iss = Issuer.from_bytes(wire.issuer_to_bytes(sp, ip, sk), max_batch=4, _binding=emu)
+    e = g["items"][0]
+    from tests.common import words
+    assert list(iss.verify_batch(PresentationBatch.from_items(bytes(e["kinds"]), words(e["words"])[None]))) == [0]
+    for bad in (sp[:-1], b"\x00\x00\x00\x00" + sp[4:], b""):
+        with pytest.raises(ValueError):
+            wire.split_system_parameters(bad)
+    nc = bytearray(sk); nc[4:36] = (wire.L).to_bytes(32, "little")
+    with pytest.raises(ValueError):
+        wire.split_secret_key(bytes(nc))
+    with pytest.raises(ValueError):
+        wire.issuer_from_bytes(blob[:-1])
