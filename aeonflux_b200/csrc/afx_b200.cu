@@ -145,6 +145,12 @@ __global__ void __launch_bounds__(128) k_ctab_setup(const u32* enc, u32 ncp, u32
         if (!ok) atomicOr(bad, 1u);
     }
 }
+__global__ void __launch_bounds__(128) k_comb_setup(const u32* enc, u32 ncp, u32* comb) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncp * COMB_WINDOWS * COMB_ENTRIES) return;
+    u32 b = t / (COMB_WINDOWS * COMB_ENTRIES), r = t % (COMB_WINDOWS * COMB_ENTRIES);
+    comb_entry_job(enc + 8 * b, r / COMB_ENTRIES, r % COMB_ENTRIES + 1, comb + (size_t)t * 24);
+}
 __global__ void k_secret_setup(const u32* secsc, u32 nsec, u32* secdig, const u32* Wenc, u32* W_pniels, u32* bad) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nsec) {
@@ -247,6 +253,10 @@ static void be_launch_verdict(const Workspace& ws, uint8_t* verdicts, be_stream 
 static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d_encneg, u32* d_bad, be_stream s) {
     u32 total = ncp * CTAB_ENTRIES;
     k_ctab_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_ctabs, d_encneg, d_bad);
+}
+static void be_launch_comb_setup(const u32* d_enc, u32 ncp, u32* d_comb, be_stream s) {
+    u32 total = ncp * COMB_WINDOWS * COMB_ENTRIES;
+    k_comb_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_comb);
 }
 static void be_launch_secret_setup(const u32* d_secsc, u32 nsec, u32* d_secdig, const u32* d_Wenc, u32* d_W, u32* d_bad, be_stream s) {
     k_secret_setup<<<1, 64, 0, s>>>(d_secsc, nsec, d_secdig, d_Wenc, d_W, d_bad);

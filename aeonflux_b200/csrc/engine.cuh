@@ -36,7 +36,11 @@ struct ScalarSrc { u16 op, f0, f1, f2; };
 
 struct VarTerm { u16 table_slot; u16 neg; ScalarSrc s; };
 struct ConstTerm { u16 ctab; u16 neg; ScalarSrc s; };
-enum : u32 { MSM_ADD_W = 1 };   // flags: add the issuer's W after the ladder (Amac::compute_V, amacs.rs:267)
+// flags.  MSM_ADD_W: add the issuer's W after the ladder (Amac::compute_V, amacs.rs:267).  MSM_COMB: a job with constant
+// bases only is evaluated on the per-issuer radix-16 comb tables ((e * 16^i) * G for every window i): 64 mixed adds per
+// term and no doublings at all.
+enum : u32 { MSM_ADD_W = 1, MSM_COMB = 2 };
+constexpr int COMB_WINDOWS = 64, COMB_ENTRIES = 8;   // comb[g][i][e-1] = (e * 16^i) * G_g in affine Niels form, 48 KiB per generator
 struct MsmDesc {
     u16 nvar, ncon, out_slot, flags;
     VarTerm var[MAX_VAR_TERMS];
@@ -96,6 +100,7 @@ struct Workspace {
     u32* derived;        // [n_derived][count][8]  per-item derived scalars (Issuer::issue only)
     // per-issuer constants
     const u32* ctabs;    // [n_ctab][128][24]  affine Niels multiples 1..128
+    const u32* comb;     // [n_ctab][64][8][24]  radix-16 comb: (e * 16^i) * G
     const u32* secdig;   // [n_secret][8]      radix-16 recoded secret scalars (packed nibbles)
     const u32* secsc;    // [n_secret][8]      the same scalars, canonical words
     const u32* W_pniels; // [32]               W in projective Niels form
@@ -371,6 +376,27 @@ struct CtabResolver {
 // (shared-memory staged on the device, global otherwise).
 template <typename CtabOf>
 AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, CtabOf ctab_of, bool active = true) {
+    if (d.flags & MSM_COMB) {      // constant bases only: radix-16 comb, public digits index it directly, no doublings
+        ge acc = ge_identity();
+        for (u32 k = 0; k < d.ncon; k++) {
+            u32 rec[8];
+            sc_recode16(rec, eval_scalar(ws, d.con[k].s, item));
+            const u32* comb = ws.comb + (size_t)d.con[k].ctab * COMB_WINDOWS * COMB_ENTRIES * 24;
+            for (int i = 0; i < COMB_WINDOWS; i++) {
+                int dig = sc_digit16(rec, i);
+                if (dig != 0) {
+                    u32 neg = ((u32)dig >> 31) ^ d.con[k].neg;
+                    u32 mag = (u32)(dig < 0 ? -dig : dig);
+                    aniels e = aniels_cneg(load_aniels(comb + ((size_t)i * COMB_ENTRIES + (mag - 1)) * 24), neg);
+                    GE_LADDER_MADD(acc, e);
+                }
+            }
+        }
+        u32 w[8];
+        ge_compress(w, acc);
+        if (active) store8(commit_ptr(ws, d.out_slot, item), w);
+        return;
+    }
     for (u32 k = 0; k < d.nvar; k++) {
         u32 rec[8];
         sc_recode16(rec, eval_scalar(ws, d.var[k].s, item));
@@ -423,6 +449,23 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
 // stream nor the address stream depends on a scalar (dalek's constant-time `*` / multiscalar_mul, amacs.rs:267-270,
 // zkp prove_compact).  scratch: (nvar + ncon) * 8 words per item.
 AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, bool active = true) {
+    if (d.flags & MSM_COMB) {      // constant bases only: radix-16 comb with constant-address scans, no doublings
+        ge acc = ge_identity();
+        for (u32 k = 0; k < d.ncon; k++) {
+            u32 rec[8];
+            sc_recode16(rec, eval_scalar(ws, d.con[k].s, item));
+            const u32* comb = ws.comb + (size_t)d.con[k].ctab * COMB_WINDOWS * COMB_ENTRIES * 24;
+            for (int i = 0; i < COMB_WINDOWS; i++) {
+                aniels e = aniels_scan_select8(comb + (size_t)i * COMB_ENTRIES * 24, sc_digit16(rec, i), d.con[k].neg);
+                GE_LADDER_MADD(acc, e);
+            }
+            for (int i = 0; i < 8; i++) rec[i] = 0;
+        }
+        u32 w[8];
+        ge_compress(w, acc);
+        if (active) store8(commit_ptr(ws, d.out_slot, item), w);
+        return;
+    }
     for (u32 k = 0; k < (u32)d.nvar + d.ncon; k++) {
         u32 rec[8];
         sc_recode16(rec, eval_scalar(ws, k < d.nvar ? d.var[k].s : d.con[k - d.nvar].s, item));
@@ -549,6 +592,25 @@ AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words
     store_fe(out + 8, fe_sub(y, x));
     store_fe(out + 16, fe_mul(fe_mul(x, y), FE_D2()));
     return ok;
+}
+
+// entry (base b, window i, multiple e in 1..8) of the radix-16 comb: (e * 16^i) * P in affine Niels form.
+AFX_HD void comb_entry_job(const u32* enc /*8 words*/, u32 i, u32 e, u32* out /*24 words*/) {
+    ge p; ge_decompress(p, enc);
+    pniels pn = ge_to_pniels(p);
+    ge acc = ge_identity();
+    for (int bit = 3; bit >= 0; bit--) {
+        acc = ge_dbl(acc, true);
+        if ((e >> bit) & 1u) acc = ge_add_pn(acc, pn, true);
+    }
+    for (u32 k = 0; k < 4 * i; k++) acc = ge_dbl(acc, true);
+    fe z = acc.Z;
+    fe t = fe_sqn(fe_pow_p58(z), 3);
+    fe zinv = fe_mul(t, fe_mul(fe_sq(z), z));
+    fe x = fe_mul(acc.X, zinv), y = fe_mul(acc.Y, zinv);
+    store_fe(out, fe_add(y, x));
+    store_fe(out + 8, fe_sub(y, x));
+    store_fe(out + 16, fe_mul(fe_mul(x, y), FE_D2()));
 }
 
 }  // namespace afx

@@ -164,6 +164,12 @@ struct MsmBuilder {
     }
 };
 
+// A job with constant bases only runs on the comb tables when 64 mixed adds per term beat 252 shared doublings + 32 per term
+// (fewer than 7 terms).
+inline void mark_comb_jobs(ShapeProgram& P) {
+    for (MsmDesc& d : P.msms) if (d.nvar == 0 && d.ncon > 0 && d.ncon < 7 && !(d.flags & MSM_ADD_W)) d.flags |= MSM_COMB;
+}
+
 // Fold the hole-free leading blocks into a midstate, append the rest to the program.
 inline void finish_transcript(ShapeProgram& P, TxBuilder& tb, u32 chal_field, u32 out_slot) {
     TxDesc d; std::memset(&d, 0, sizeof d);
@@ -329,6 +335,7 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         finish_transcript(P, tb, b, (u32)(1 + e));
     }
     P.n_msm = slot; P.n_proofs = (u32)P.txs.size();
+    mark_comb_jobs(P);
     return P;
 }
 
@@ -387,6 +394,7 @@ inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const
     tb.challenge();
     finish_transcript(P, tb, F_CHAL, 0);
     P.n_msm = slot; P.n_proofs = 1;
+    mark_comb_jobs(P);
     return P;
 }
 
@@ -476,6 +484,7 @@ inline ShapeProgram compile_issue(const IssuerConsts& ic, u32 n, const uint8_t* 
     for (u32 i = 0; i < n; i++) O.resp_sec[4 + i] = (u16)sec_y(i);
     O.resp_sec[4 + n] = 0xffff;
     for (u32 k = 0; k < n + 5; k++) O.resp_blind[k] = (u16)D_B(k);
+    mark_comb_jobs(P);
     return P;
 }
 

@@ -74,6 +74,28 @@ static void be_launch_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encne
         ge p; ge_decompress(p, enc + 8 * b); ge_compress(encneg + 8 * b, ge_neg(p));
     }
 }
+static void be_launch_comb_setup(const u32* enc, u32 ncp, u32* comb, be_stream) {
+    // same entries as comb_entry_job, walked window by window (16 * previous) instead of from scratch: the emulation runs on one core
+    for (u32 b = 0; b < ncp; b++) {
+        ge p; ge_decompress(p, enc + 8 * b);
+        pniels pn = ge_to_pniels(p);
+        ge mult[COMB_ENTRIES];
+        mult[0] = p;
+        for (int e = 1; e < COMB_ENTRIES; e++) mult[e] = ge_add_pn(mult[e - 1], pn, true);
+        for (int i = 0; i < COMB_WINDOWS; i++) {
+            for (int e = 0; e < COMB_ENTRIES; e++) {
+                ge& a = mult[e];
+                fe z = a.Z;
+                fe t = fe_sqn(fe_pow_p58(z), 3);
+                fe zinv = fe_mul(t, fe_mul(fe_sq(z), z));
+                fe x = fe_mul(a.X, zinv), y = fe_mul(a.Y, zinv);
+                u32* out = comb + (((size_t)b * COMB_WINDOWS + i) * COMB_ENTRIES + e) * 24;
+                store_fe(out, fe_add(y, x)); store_fe(out + 8, fe_sub(y, x)); store_fe(out + 16, fe_mul(fe_mul(x, y), FE_D2()));
+                for (int k = 0; k < 4; k++) a = ge_dbl(a, true);
+            }
+        }
+    }
+}
 static void be_launch_secret_setup(const u32* secsc, u32 nsec, u32* secdig, const u32* Wenc, u32* W, u32* bad, be_stream) {
     for (u32 t = 0; t < nsec; t++) { sc s = sc_from_words(secsc + 8 * t); if (!sc_is_canonical(s)) *bad |= 2; sc_recode16(secdig + 8 * t, s); }
     ge p; if (!ge_decompress(p, Wenc)) *bad |= 1;
