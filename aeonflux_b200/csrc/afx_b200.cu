@@ -111,14 +111,14 @@ __global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_msm_ct(Workspace ws, 
     msm_ct_job(ws, d, item, smem + threadIdx.x, blockDim.x, active);
 }
 
-__global__ void __launch_bounds__(256) k_derive(Workspace ws, const WideDesc* d) {
+__global__ void __launch_bounds__(256) k_derive(Workspace ws, const DeriveOp* ops, u32 nops) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < ws.count) derive_job(ws, d[blockIdx.y], blockIdx.y, item);
+    if (item < ws.count) derive_program_job(ws, ops, nops, item);
 }
 
-__global__ void __launch_bounds__(256) k_issue_out(Workspace ws, const IssueOutDesc* d, u32* out) {
+__global__ void __launch_bounds__(256) k_out_words(Workspace ws, const OutWord* d, u32* out) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < ws.count) issue_out_job(ws, *d, blockIdx.y, item, out);
+    if (item < ws.count) out_word_job(ws, d[blockIdx.y], blockIdx.y, item, out);
 }
 
 __global__ void __launch_bounds__(TPB) k_transcript(Workspace ws, const TxDesc* txs) {
@@ -238,11 +238,11 @@ static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* d_msms, const u
     if (!attr_set) { cudaFuncSetAttribute(k_msm_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
     k_msm_ct<<<grid_for(ws.count, tpb, nidx), tpb, smem, s>>>(ws, d_msms, d_idx);
 }
-static void be_launch_derive(const Workspace& ws, const WideDesc* d, u32 nd, be_stream s) {
-    k_derive<<<grid_for(ws.count, 256, nd), 256, 0, s>>>(ws, d);
+static void be_launch_derive(const Workspace& ws, const DeriveOp* d, u32 nd, be_stream s) {
+    k_derive<<<grid_for(ws.count, 256, 1), 256, 0, s>>>(ws, d, nd);
 }
-static void be_launch_issue_out(const Workspace& ws, const IssueOutDesc* d, u32 nwords, u32* out, be_stream s) {
-    k_issue_out<<<grid_for(ws.count, 256, nwords), 256, 0, s>>>(ws, d, out);
+static void be_launch_out_words(const Workspace& ws, const OutWord* d, u32 nwords, u32* out, be_stream s) {
+    k_out_words<<<grid_for(ws.count, 256, nwords), 256, 0, s>>>(ws, d, out);
 }
 static void be_launch_transcript(const Workspace& ws, const TxDesc* d_txs, u32 ntx, be_stream s) {
     k_transcript<<<grid_for(ws.count, TPB, ntx), TPB, 0, s>>>(ws, d_txs);

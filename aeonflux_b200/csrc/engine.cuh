@@ -39,10 +39,11 @@ struct ConstTerm { u16 ctab; u16 neg; ScalarSrc s; };
 // flags.  MSM_ADD_W: add the issuer's W after the ladder (Amac::compute_V, amacs.rs:267).  MSM_COMB: a job with constant
 // bases only is evaluated on the per-issuer radix-16 comb tables ((e * 16^i) * G for every window i): 64 mixed adds per
 // term and no doublings at all.
-enum : u32 { MSM_ADD_W = 1, MSM_COMB = 2 };
+enum : u32 { MSM_ADD_W = 1, MSM_COMB = 2, MSM_ADD_EXT = 4 };
 constexpr int COMB_WINDOWS = 64, COMB_ENTRIES = 8;   // comb[g][i][e-1] = (e * 16^i) * G_g in affine Niels form, 48 KiB per generator
 struct MsmDesc {
     u16 nvar, ncon, out_slot, flags;
+    u16 add_ext, pad;                  // MSM_ADD_EXT: ext slot of a per-item point added after the ladder
     VarTerm var[MAX_VAR_TERMS];
     ConstTerm con[MAX_CONST_TERMS];
 };
@@ -75,13 +76,18 @@ struct TxDesc {
     u64 midstate[25];
 };
 
-// Issuer::issue epilogue (issuer.rs:111-124 / zkp prove_compact): output words t, U, V, challenge, responses[n+5]
-struct WideDesc { u16 lo, hi; };                       // derived scalar k = (F[lo] || F[hi]) mod l  (Scalar::random's wide reduction)
-struct IssueOutDesc {
-    u16 nresp, comp_U, commit_V, der_t;
-    u16 resp_sec[MAX_ATTRS + 5];                       // secret row of witness k, 0xffff = the constant scalar "1"
-    u16 resp_blind[MAX_ATTRS + 5];                     // derived slot of blinding k
-};
+// Prover paths (Issuer::issue, AnonymousCredential::show): per-item derived scalars and the output words.
+// Derived slot k = result of op k, evaluated in order by one thread per item (operands are scalar refs, so an op may use
+// the slots before it).
+enum : u32 { DV_WIDE = 0, DV_MUL = 1, DV_MULADD = 2, DV_NEGMUL = 3 };
+// DV_WIDE:   (F[a] || F[b]) mod l           Scalar::random's wide reduction of 64 rng bytes
+// DV_MUL:    R[a] * R[b]        DV_MULADD: R[a] + R[b] * R[c]        DV_NEGMUL: -(R[a] * R[b])
+struct DeriveOp { u16 op, a, b, c; };
+// One 32-byte output word per (item, OutWord).
+enum : u32 { OW_FIELD = 0, OW_COMP = 1, OW_COMMIT = 2, OW_DERIVED = 3, OW_CHAL = 4, OW_RESP = 5 };
+// OW_RESP: a = proof index, b = witness scalar ref (0xffff = the constant "1"), c = blinding scalar ref:
+//          response = witness * challenge + blinding  (zkp prove_compact)
+struct OutWord { u16 kind, a, b, c; };
 
 // ---- workspace ------------------------------------------------------------------------------------
 // All arrays are slot-major then item-major; an item's 32-byte word is 8 consecutive u32 (two 128-bit loads).
@@ -461,6 +467,7 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
             }
             for (int i = 0; i < 8; i++) rec[i] = 0;
         }
+        if (d.flags & MSM_ADD_EXT) acc = ge_add(acc, load_ge(ext_ptr(ws, d.add_ext, item)));
         u32 w[8];
         ge_compress(w, acc);
         if (active) store8(commit_ptr(ws, d.out_slot, item), w);
@@ -492,36 +499,46 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
     }
     for (u32 k = 0; k < ((u32)d.nvar + d.ncon) * 8; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded secrets
     if (d.flags & MSM_ADD_W) acc = ge_add_pn(acc, load_pniels(ws.W_pniels));
+    if (d.flags & MSM_ADD_EXT) acc = ge_add(acc, load_ge(ext_ptr(ws, d.add_ext, item)));
     u32 w[8];
     ge_compress(w, acc);
     if (active) store8(commit_ptr(ws, d.out_slot, item), w);
 }
 
-// ---- stage: derived scalars (Issuer::issue) ------------------------------------------------------------------------
-// Scalar::random(rng) = 64 rng bytes reduced mod l (amacs.rs:289; zkp prove_compact's blindings)
-AFX_HD void derive_job(const Workspace& ws, const WideDesc& d, u32 slot, u32 item) {
-    u32 x[16];
-    load8(x, field_ptr(ws, d.lo, item)); load8(x + 8, field_ptr(ws, d.hi, item));
-    sc r = sc_reduce512(x);
-    store8(ws.derived + ((size_t)slot * ws.count + item) * 8, r.v);
+// ---- stage: derived scalars (prover paths) ---------------------------------------------------------------------------
+AFX_HD void derive_program_job(const Workspace& ws, const DeriveOp* ops, u32 nops, u32 item) {
+    for (u32 k = 0; k < nops; k++) {
+        const DeriveOp& d = ops[k];
+        sc r;
+        if (d.op == DV_WIDE) {     // Scalar::random(rng) = 64 rng bytes reduced mod l (amacs.rs:289; zkp prove_compact's blindings)
+            u32 x[16];
+            load8(x, field_ptr(ws, d.a, item)); load8(x + 8, field_ptr(ws, d.b, item));
+            r = sc_reduce512(x);
+        } else {
+            sc a = load_sc(scalar_ref_ptr(ws, d.a, item)), b = load_sc(scalar_ref_ptr(ws, d.b, item));
+            if (d.op == DV_MUL) r = sc_mul(a, b);
+            else if (d.op == DV_NEGMUL) r = sc_neg(sc_mul(a, b));
+            else r = sc_muladd(b, load_sc(scalar_ref_ptr(ws, d.c, item)), a);
+        }
+        store8(ws.derived + ((size_t)k * ws.count + item) * 8, r.v);
+    }
 }
 
-// ---- stage: issuance output ----------------------------------------------------------------------------------------
-// word 0 = t, 1 = U, 2 = V, 3 = challenge, 4 + k = response k = witness_k * c + blinding_k (zkp prove_compact).
+// ---- stage: prover output --------------------------------------------------------------------------------------------
 // A request the Rust types could never hold (status != 0) yields all-zero words.
-AFX_HD void issue_out_job(const Workspace& ws, const IssueOutDesc& d, u32 word, u32 item, u32* out /*[nresp+4][count][8]*/) {
+AFX_HD void out_word_job(const Workspace& ws, const OutWord& d, u32 word, u32 item, u32* out /*[n_out][count][8]*/) {
     u32 w[8];
     if (ws.status[item] != 0) { for (int i = 0; i < 8; i++) w[i] = 0; }
-    else if (word == 0) load8(w, scalar_ref_ptr(ws, SREF_DERIVED | d.der_t, item));
-    else if (word == 1) load8(w, comp_ptr(ws, d.comp_U, item));
-    else if (word == 2) load8(w, commit_ptr(ws, d.commit_V, item));
-    else if (word == 3) load8(w, ws.chal + (size_t)item * 8);
+    else if (d.kind == OW_FIELD) load8(w, field_ptr(ws, d.a, item));
+    else if (d.kind == OW_COMP) load8(w, comp_ptr(ws, d.a, item));
+    else if (d.kind == OW_COMMIT) load8(w, commit_ptr(ws, d.a, item));
+    else if (d.kind == OW_DERIVED) load8(w, scalar_ref_ptr(ws, SREF_DERIVED | d.a, item));
+    else if (d.kind == OW_CHAL) load8(w, ws.chal + ((size_t)d.a * ws.count + item) * 8);
     else {
-        u32 k = word - 4;
-        sc c = load_sc(ws.chal + (size_t)item * 8);
-        sc b = load_sc(scalar_ref_ptr(ws, SREF_DERIVED | d.resp_blind[k], item));
+        sc c = load_sc(ws.chal + ((size_t)d.a * ws.count + item) * 8);
+        sc b = load_sc(scalar_ref_ptr(ws, d.c, item));
         sc s;
-        if (d.resp_sec[k] == 0xffff) { s = sc_zero(); s.v[0] = 1; } else s = load_sc(ws.secsc + 8 * d.resp_sec[k]);
+        if (d.b == 0xffff) { s = sc_zero(); s.v[0] = 1; } else s = load_sc(scalar_ref_ptr(ws, d.b, item));
         sc r = sc_muladd(s, c, b);
         for (int i = 0; i < 8; i++) w[i] = r.v[i];
     }

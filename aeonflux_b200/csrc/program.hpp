@@ -129,8 +129,8 @@ struct TxBuilder {
 struct ShapeProgram {
     u32 n_fields = 0, n_tables = 0, n_atabs = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
     bool is_issue = false;             // Issuer::issue: constant-schedule MSMs, derived scalars, output words instead of verdicts
-    std::vector<WideDesc> derived;
-    IssueOutDesc issue_out{};
+    std::vector<DeriveOp> derived;     // per-item derived scalars, slot k = op k
+    std::vector<OutWord> out_words;    // prover output words
     std::vector<u16> scalar_fields;
     std::vector<PointJob> point_jobs;
     bool has_amac = false;
@@ -154,6 +154,7 @@ inline ScalarSrc sc_muladd3(u32 a, u32 b, u32 c) { ScalarSrc s; s.op = SC_MULADD
 struct MsmBuilder {
     MsmDesc d{};
     explicit MsmBuilder(u32 out_slot) { std::memset(&d, 0, sizeof d); d.out_slot = (u16)out_slot; }
+    void add_ext(u32 ext_slot) { d.flags |= MSM_ADD_EXT; d.add_ext = (u16)ext_slot; }
     void var(u32 table_slot, ScalarSrc s, bool neg = false) {
         if (d.nvar >= MAX_VAR_TERMS) throw std::length_error("too many variable-base terms");
         VarTerm& t = d.var[d.nvar++]; t.table_slot = (u16)table_slot; t.neg = neg; t.s = s;
@@ -414,8 +415,9 @@ inline ShapeProgram compile_issue(const IssuerConsts& ic, u32 n, const uint8_t* 
     // derived scalars: slot 0 = t, 1 + k = blinding k
     const u32 D_T = 0;
     auto D_B = [](u32 k) { return 1 + k; };
-    { WideDesc w; w.lo = (u16)F_TSEED; w.hi = (u16)(F_TSEED + 1); P.derived.push_back(w); }
-    for (u32 k = 0; k < n + 5; k++) { WideDesc w; w.lo = (u16)(F_BSEED + 2 * k); w.hi = (u16)(F_BSEED + 2 * k + 1); P.derived.push_back(w); }
+    auto wide = [&](u32 lo) { DeriveOp w; w.op = DV_WIDE; w.a = (u16)lo; w.b = (u16)(lo + 1); w.c = 0; P.derived.push_back(w); };
+    wide(F_TSEED);
+    for (u32 k = 0; k < n + 5; k++) wide(F_BSEED + 2 * k);
     const u32 B_w = D_B(0), B_wp = D_B(1), B_x0 = D_B(2), B_x1 = D_B(3), B_one = D_B(4 + n);
     auto B_y = [&](u32 i) { return D_B(4 + i); };
     const u32 S_w = sref_secret(2 + n), S_wp = sref_secret(3 + n), S_x0 = sref_secret(sec_x0()), S_x1 = sref_secret(sec_x1());
@@ -477,13 +479,181 @@ inline ShapeProgram compile_issue(const IssuerConsts& ic, u32 n, const uint8_t* 
     tb.challenge();
     finish_transcript(P, tb, 0xffff, 0);
     P.n_msm = slot; P.n_proofs = 1;
-    IssueOutDesc& O = P.issue_out; std::memset(&O, 0, sizeof O);
-    O.nresp = (u16)(n + 5); O.comp_U = (u16)C_U; O.commit_V = (u16)S_V; O.der_t = (u16)D_T;
-    const u32 rows[4] = {2 + n, 3 + n, sec_x0(), sec_x1()};
-    for (u32 k = 0; k < 4; k++) O.resp_sec[k] = (u16)rows[k];
-    for (u32 i = 0; i < n; i++) O.resp_sec[4 + i] = (u16)sec_y(i);
-    O.resp_sec[4 + n] = 0xffff;
-    for (u32 k = 0; k < n + 5; k++) O.resp_blind[k] = (u16)D_B(k);
+    auto word = [&](u32 kind, u32 a, u32 b = 0, u32 c = 0) { OutWord o; o.kind = (u16)kind; o.a = (u16)a; o.b = (u16)b; o.c = (u16)c; P.out_words.push_back(o); };
+    word(OW_DERIVED, D_T); word(OW_COMP, C_U); word(OW_COMMIT, S_V); word(OW_CHAL, 0);
+    const u32 wit[4] = {sref_secret(2 + n), sref_secret(3 + n), sref_secret(sec_x0()), sref_secret(sec_x1())};   // w, w', x_0, x_1
+    for (u32 k = 0; k < 4; k++) word(OW_RESP, 0, wit[k], sref_derived(D_B(k)));
+    for (u32 i = 0; i < n; i++) word(OW_RESP, 0, sref_secret(sec_y(i)), sref_derived(D_B(4 + i)));
+    word(OW_RESP, 0, 0xffff, sref_derived(D_B(4 + n)));                                                          // the witness "1"
+    mark_comb_jobs(P);
+    return P;
+}
+
+// AnonymousCredential::show as a program (credential.rs:37-46 -> ProofOfValidCredential::prove presentation.rs:139-321 and, per
+// hidden plaintext attribute, ProofOfEncryption::prove encryption.rs:58-142 with Keypair::encrypt symmetric.rs:252-261),
+// with the rng output supplied by the caller.  The user-side batch operation: it needs no issuer secret.
+// kinds = the presentation's attribute kinds (0 revealed scalar, 1 hidden scalar, 2 revealed point, 3 hidden plaintext).
+// Fields: t, U, V, then per attribute: scalar m_i (kinds 0/1) | point M_i (kind 2) | plaintext M1, M2, m3 (kind 3);
+//         then a, a0, a1, pk of the symmetric keypair (only if some kind is 3); then two 32-byte words (64 rng bytes) per
+//         random value: z, the main proof's 3 + h_s blindings, then 6 blindings per hidden plaintext.
+// Output words: exactly the presentation layout of include/aeonflux_b200.h.
+// Every commitment is rewritten over the per-issuer generators and the *input* points (U, M2): e.g. the blinding commitment
+// b_t*C_x_0 + b_z0*G_x_0 + b_z*G_x_1 with C_x_0 = z*G_x_0 + U becomes (b_z0 + b_t*z)*G_x_0 + b_z*G_x_1 + b_t*U, so no ladder
+// has to wait for another ladder's output and every job of an item runs in one launch.
+inline size_t show_num_fields(u32 n, const uint8_t* kinds) {
+    size_t f = 3, hs = 0, hp = 0;
+    for (u32 i = 0; i < n; i++) { f += kinds[i] == 3 ? 3 : 1; hs += kinds[i] == 1; hp += kinds[i] == 3; }
+    return f + (hp ? 4 : 0) + 2 + 2 * (3 + hs) + 12 * hp;
+}
+inline ShapeProgram compile_show(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+    if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
+    for (u32 i = 0; i < n; i++) if (kinds[i] > 3) throw std::invalid_argument("bad attribute kind");
+    ShapeProgram P; P.is_issue = true;
+    u32 hs = 0, hp = 0; std::vector<int> ss_rank(n, -1);
+    for (u32 i = 0; i < n; i++) { if (kinds[i] == 1) ss_rank[i] = (int)hs++; hp += kinds[i] == 3; }
+    // ---- field map
+    const u32 F_T = 0, F_U = 1, F_V = 2;
+    u32 f = 3;
+    std::vector<u32> F_ATTR(n);
+    for (u32 i = 0; i < n; i++) { F_ATTR[i] = f; f += kinds[i] == 3 ? 3 : 1; }
+    u32 F_A = 0, F_A0 = 0, F_A1 = 0, F_PK = 0;
+    if (hp) { F_A = f++; F_A0 = f++; F_A1 = f++; F_PK = f++; }
+    const u32 F_ZSEED = f; f += 2;
+    const u32 F_BSEED = f; f += 2 * (3 + hs);
+    const u32 F_EBSEED = f; f += 12 * hp;
+    P.n_fields = f;
+    P.scalar_fields.push_back((u16)F_T);
+    for (u32 i = 0; i < n; i++) { if (kinds[i] <= 1) P.scalar_fields.push_back((u16)F_ATTR[i]); if (kinds[i] == 3) P.scalar_fields.push_back((u16)(F_ATTR[i] + 2)); }
+    if (hp) for (u32 k : {F_A, F_A0, F_A1}) P.scalar_fields.push_back((u16)k);
+    // ---- derived scalars
+    auto dv = [&](u32 op, u32 a, u32 b, u32 c = 0) { DeriveOp d; d.op = (u16)op; d.a = (u16)a; d.b = (u16)b; d.c = (u16)c; P.derived.push_back(d); return sref_derived((u32)P.derived.size() - 1); };
+    auto wide = [&](u32 lo) { return dv(DV_WIDE, lo, lo + 1); };
+    const u32 D_z = wide(F_ZSEED);
+    const u32 D_z0 = dv(DV_NEGMUL, F_T, D_z);                                   // z_0 = -t*z (presentation.rs:163)
+    const u32 D_bz = wide(F_BSEED), D_bz0 = wide(F_BSEED + 2), D_bt = wide(F_BSEED + 4);
+    std::vector<u32> D_bm(hs);
+    for (u32 k = 0; k < hs; k++) D_bm[k] = wide(F_BSEED + 6 + 2 * k);
+    const u32 D_g0 = dv(DV_MULADD, D_bz0, D_bt, D_z);                            // b_z0 + b_t*z
+    // ---- points
+    u32 natab = 0, next = 0;
+    auto pjob = [&](u32 field, bool atab, bool ext, int* a_out, int* e_out) {
+        PointJob j; j.field_a = (int16_t)field; j.field_b = -1; j.op = PJ_COPY; j.table_slot = -1; j.comp_slot = -1; j.compneg_slot = -1;
+        j.atab_slot = (int16_t)(atab ? (int)natab++ : -1); j.ext_slot = (int16_t)(ext ? (int)next++ : -1);
+        if (a_out) *a_out = j.atab_slot; if (e_out) *e_out = j.ext_slot;
+        P.point_jobs.push_back(j);
+    };
+    int A_U, E_U, E_V;
+    pjob(F_U, true, true, &A_U, &E_U); pjob(F_V, false, true, nullptr, &E_V);
+    std::vector<int> E_M1(n, -1), A_M2(n, -1), E_M2(n, -1);
+    for (u32 i = 0; i < n; i++) {
+        if (kinds[i] == 2) pjob(F_ATTR[i], false, false, nullptr, nullptr);     // revealed point: only has to decode
+        if (kinds[i] == 3) { pjob(F_ATTR[i], false, true, nullptr, &E_M1[i]); pjob(F_ATTR[i] + 1, true, true, &A_M2[i], &E_M2[i]); }
+    }
+    if (hp) pjob(F_PK, false, false, nullptr, nullptr);
+    P.n_tables = 0; P.n_atabs = natab; P.n_ext = next; P.n_comp = 0;
+    // ---- ladders (every scalar is a user secret: constant-schedule jobs; a variable term's table_slot is its transposed table)
+    u32 slot = 0;
+    auto push = [&](MsmBuilder& m) { P.msms.push_back(m.d); return slot++; };
+    auto R = [](u32 ref) { return sc_field(ref); };
+    u32 S_CX0, S_CX1, S_CV, S_Z, S_RZ, S_RCX1;
+    { MsmBuilder m(slot); m.con(ic.id_Gx0(), R(D_z)); m.add_ext((u32)E_U); S_CX0 = push(m); }                              // C_x_0 = z*G_x_0 + U   (:181)
+    { MsmBuilder m(slot); m.var((u32)A_U, R(F_T)); m.con(ic.id_Gx1(), R(D_z)); S_CX1 = push(m); }                          // C_x_1 = z*G_x_1 + t*U (:182)
+    { MsmBuilder m(slot); m.con(ic.id_GV(), R(D_z)); m.add_ext((u32)E_V); S_CV = push(m); }                                // C_V = z*G_V + V       (:183)
+    std::vector<u32> S_CY(n);
+    for (u32 i = 0; i < n; i++) {                                                                                           // (:169-180)
+        MsmBuilder m(slot); m.con(ic.id_Gy(i), R(D_z));
+        if (kinds[i] == 1) m.con(ic.id_Gm(i), R(F_ATTR[i]));
+        if (kinds[i] == 3) m.add_ext((u32)E_M1[i]);
+        S_CY[i] = push(m);
+    }
+    { MsmBuilder m(slot); m.con(ic.id_I(), R(D_z)); S_Z = push(m); }                                                       // Z = z*I (:184)
+    { MsmBuilder m(slot); m.con(ic.id_I(), R(D_bz)); S_RZ = push(m); }
+    { MsmBuilder m(slot); m.var((u32)A_U, R(D_bt)); m.con(ic.id_Gx0(), R(D_g0)); m.con(ic.id_Gx1(), R(D_bz)); S_RCX1 = push(m); }
+    std::vector<u32> nsp;
+    for (u32 i = 0; i < n; i++) if (kinds[i] != 3) nsp.push_back(i);
+    struct Con { u32 slot; const char* label; };
+    std::vector<Con> main_cons; main_cons.push_back({S_RZ, "Z"}); main_cons.push_back({S_RCX1, "C_x_1"});
+    for (u32 i = 0; i < nsp.size(); i++) {                    // compacted-index loop (:267-273)
+        if (kinds[i] == 3) continue;
+        MsmBuilder m(slot); m.con(ic.id_Gy(i), R(D_bz));
+        if (kinds[i] == 1) m.con(ic.id_Gm(i), R(D_bm[ss_rank[i]]));
+        main_cons.push_back({push(m), "C_y"});
+    }
+    {
+        TxBuilder tb; tb.start("2019/1416 anonymous credential"); tb.domain_sep("2019/1416 presentation proof");
+        tb.scalar_var("z"); tb.scalar_var("z_0"); tb.scalar_var("t");
+        for (u32 k = 0; k < hs; k++) tb.scalar_var("m");
+        tb.point_var_const("I", ic.enc[ic.id_I()].data());
+        tb.point_var("C_x_1", SRC_COMMIT, S_CX1, false); tb.point_var("C_x_0", SRC_COMMIT, S_CX0, false);
+        tb.point_var_const("G_x_0", ic.enc[ic.id_Gx0()].data()); tb.point_var_const("G_x_1", ic.enc[ic.id_Gx1()].data());
+        for (u32 i : nsp) tb.point_var("C_y", SRC_COMMIT, S_CY[i], false);
+        for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("G_y", ic.enc[ic.id_Gy(i)].data());
+        for (u32 i = 0; i < n; i++) if (kinds[i] == 1) tb.point_var_const("G_m", ic.enc[ic.id_Gm(i)].data());
+        tb.point_var("Z", SRC_COMMIT, S_Z, false);
+        for (const Con& c : main_cons) { tb.blinding_commitment(c.label, c.slot); P.dump_commit.push_back(c.slot); }
+        tb.challenge();
+        finish_transcript(P, tb, 0xffff, 0);
+    }
+    auto word = [&](u32 kind, u32 a, u32 b = 0, u32 c = 0) { OutWord o; o.kind = (u16)kind; o.a = (u16)a; o.b = (u16)b; o.c = (u16)c; P.out_words.push_back(o); };
+    word(OW_CHAL, 0);
+    word(OW_RESP, 0, D_z, D_bz); word(OW_RESP, 0, D_z0, D_bz0); word(OW_RESP, 0, F_T, D_bt);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 1) word(OW_RESP, 0, F_ATTR[i], D_bm[ss_rank[i]]);
+    word(OW_COMMIT, S_CX0); word(OW_COMMIT, S_CX1); word(OW_COMMIT, S_CV);
+    for (u32 i = 0; i < n; i++) word(OW_COMMIT, S_CY[i]);
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0 || kinds[i] == 2) word(OW_FIELD, F_ATTR[i]);
+    // ---- proofs of encryption, one per hidden plaintext (presentation.rs:293-309 -> encryption.rs:58-142)
+    u32 e = 0;
+    for (u32 idx = 0; idx < n; idx++) {
+        if (kinds[idx] != 3) continue;
+        const u32 F_M3 = F_ATTR[idx] + 2, AM2 = (u32)A_M2[idx], EM1 = (u32)E_M1[idx], EM2 = (u32)E_M2[idx];
+        const u32 D_u = dv(DV_MULADD, F_A0, F_A1, F_M3);                        // a0 + a1*m3 (symmetric.rs:257)
+        const u32 D_au = dv(DV_MUL, F_A, D_u);
+        const u32 D_z1 = dv(DV_NEGMUL, D_z, D_u);                                // z1 = -z*(a0 + a1*m3) (encryption.rs:78)
+        const u32 D_a1z = dv(DV_MUL, F_A1, D_z);
+        const u32 B0 = F_EBSEED + 12 * e;
+        const u32 D_ba = wide(B0), D_ba0 = wide(B0 + 2), D_ba1 = wide(B0 + 4), D_bm3 = wide(B0 + 6), D_bze = wide(B0 + 8), D_bz1 = wide(B0 + 10);
+        const u32 D_bau = dv(DV_MUL, D_ba, D_u);
+        const u32 D_ba1z = dv(DV_MUL, D_ba1, D_z);
+        const u32 D_s1 = dv(DV_MULADD, D_ba0, D_bm3, F_A1);                      // b_a0 + b_m3*a1
+        const u32 D_s2 = dv(DV_MULADD, D_bz1, D_s1, D_z);                        // b_z1 + (b_a0 + b_m3*a1)*z
+        u32 S_E1, S_E2, S_CY1, S_CY2, S_CY3, S_CY2P, S_D, S_NE1, S_Rpk, S_RD, S_RCY2P, S_RE1, S_RCY3;
+        { MsmBuilder m(slot); m.var(AM2, R(D_u)); S_E1 = push(m); }                                                         // E1 = (a0 + a1*m3)*M2
+        { MsmBuilder m(slot); m.var(AM2, R(D_au)); m.add_ext(EM1); S_E2 = push(m); }                                        // E2 = a*E1 + M1
+        { MsmBuilder m(slot); m.con(ic.id_Gy(0), R(D_z)); m.add_ext(EM1); S_CY1 = push(m); }                                // C_y_1 = z*G_y[0] + M1
+        { MsmBuilder m(slot); m.con(ic.id_Gy(1), R(D_z)); m.add_ext(EM2); S_CY2 = push(m); }                                // C_y_2 = z*G_y[1] + M2
+        { MsmBuilder m(slot); m.con(ic.id_Gy(2), R(D_z)); m.con(ic.id_Gm(idx), R(F_M3)); S_CY3 = push(m); }                 // C_y_3 = z*G_y[2] + m3*G_m[idx]
+        { MsmBuilder m(slot); m.var(AM2, R(F_A1)); m.con(ic.id_Gy(1), R(D_a1z)); S_CY2P = push(m); }                        // C_y_2' = a1*C_y_2
+        { MsmBuilder m(slot); m.con(ic.id_Gy(0), R(D_z)); m.var(AM2, R(D_au), true); S_D = push(m); }                       // C_y_1 - E2 (M1 cancels)
+        { MsmBuilder m(slot); m.var(AM2, R(D_u), true); S_NE1 = push(m); }                                                  // -E1
+        { MsmBuilder m(slot); m.con(ic.id_Ga(), R(D_ba)); m.con(ic.id_Ga0(), R(D_ba0)); m.con(ic.id_Ga1(), R(D_ba1)); S_Rpk = push(m); }
+        { MsmBuilder m(slot); m.con(ic.id_Gy(0), R(D_bze)); m.var(AM2, R(D_bau), true); S_RD = push(m); }                   // b_z*G_y_1 + b_a*(-E1)
+        { MsmBuilder m(slot); m.var(AM2, R(D_ba1)); m.con(ic.id_Gy(1), R(D_ba1z)); S_RCY2P = push(m); }                     // b_a1*C_y_2
+        { MsmBuilder m(slot); m.con(ic.id_Gy(1), R(D_s2)); m.var(AM2, R(D_s1)); S_RE1 = push(m); }                          // b_a0*C_y_2 + b_m3*C_y_2' + b_z1*G_y_2
+        { MsmBuilder m(slot); m.con(ic.id_Gy(2), R(D_bze)); m.con(ic.id_Gm(idx), R(D_bm3)); S_RCY3 = push(m); }
+        TxBuilder tb; tb.start("2019/1416 anonymous credentials"); tb.domain_sep("2019/1416 proof of encryption");
+        tb.scalar_var("a"); tb.scalar_var("a0"); tb.scalar_var("a1"); tb.scalar_var("m3"); tb.scalar_var("z"); tb.scalar_var("z1");
+        tb.point_var("pk", SRC_FIELD, F_PK, false);
+        tb.point_var_const("G_a", ic.enc[ic.id_Ga()].data()); tb.point_var_const("G_a_0", ic.enc[ic.id_Ga0()].data());
+        tb.point_var_const("G_a_1", ic.enc[ic.id_Ga1()].data());
+        tb.point_var_const("G_y_1", ic.enc[ic.id_Gy(0)].data()); tb.point_var_const("G_y_2", ic.enc[ic.id_Gy(1)].data());
+        tb.point_var_const("G_y_3", ic.enc[ic.id_Gy(2)].data()); tb.point_var_const("G_m_3", ic.enc[ic.id_Gm(idx)].data());
+        tb.point_var("C_y_2", SRC_COMMIT, S_CY2, false); tb.point_var("C_y_3", SRC_COMMIT, S_CY3, false); tb.point_var("C_y_2'", SRC_COMMIT, S_CY2P, false);
+        tb.point_var("C_y_1-E2", SRC_COMMIT, S_D, false);
+        tb.point_var("E1", SRC_COMMIT, S_E1, false);
+        tb.point_var("-E1", SRC_COMMIT, S_NE1, false);
+        tb.blinding_commitment("pk", S_Rpk); tb.blinding_commitment("C_y_1-E2", S_RD); tb.blinding_commitment("C_y_2'", S_RCY2P);
+        tb.blinding_commitment("E1", S_RE1); tb.blinding_commitment("C_y_3", S_RCY3);
+        for (u32 s2 : {S_Rpk, S_RD, S_RCY2P, S_RE1, S_RCY3}) P.dump_commit.push_back(s2);
+        tb.challenge();
+        finish_transcript(P, tb, 0xffff, 1 + e);
+        word(OW_CHAL, 1 + e);
+        word(OW_RESP, 1 + e, F_A, D_ba); word(OW_RESP, 1 + e, F_A0, D_ba0); word(OW_RESP, 1 + e, F_A1, D_ba1);
+        word(OW_RESP, 1 + e, F_M3, D_bm3); word(OW_RESP, 1 + e, D_z, D_bze); word(OW_RESP, 1 + e, D_z1, D_bz1);
+        word(OW_FIELD, F_PK);
+        word(OW_COMMIT, S_E1); word(OW_COMMIT, S_E2); word(OW_COMMIT, S_CY1); word(OW_COMMIT, S_CY2); word(OW_COMMIT, S_CY3); word(OW_COMMIT, S_CY2P);
+        e++;
+    }
+    P.n_msm = slot; P.n_proofs = (u32)P.txs.size();
     mark_comb_jobs(P);
     return P;
 }

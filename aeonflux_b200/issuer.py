@@ -194,6 +194,33 @@ class Issuer:
         res = IssuanceBatch(batch.kinds, out)
         return (res, status, dump) if debug else (res, status)
 
+    def show_batch(self, kinds, fields, debug=False):
+        """Batch AnonymousCredential::show (credential.rs:37-46).  kinds: the presentation's attribute kinds; fields: uint8
+        [afx_show_num_fields][count][32] in the order documented in include/aeonflux_b200.h (credential, attributes, keypair,
+        rng bytes).  Returns (PresentationBatch, status) -- the batch can be passed to verify_batch as is."""
+        kinds = bytes(kinds)
+        fields = np.ascontiguousarray(fields, dtype=np.uint8)
+        nf = self._b.L.afx_show_num_fields(len(kinds), kinds)
+        if fields.ndim != 3 or fields.shape[0] != nf or fields.shape[2] != 32:
+            raise ValueError("show input must be [%d][count][32] bytes for this shape" % nf)
+        count = fields.shape[1]
+        ptrs, keep = B._as_fields(fields)
+        cb = B.afx_presentation_batch(len(kinds), kinds, count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        out = np.zeros((self.num_fields(kinds), count, 32), np.uint8)
+        optrs, okeep = B._as_fields(out)
+        ob = B.afx_issuance_out(ctypes.cast(optrs, ctypes.POINTER(ctypes.c_void_p)), len(okeep))
+        status = np.zeros(count, np.uint8)
+        dbg, dump = None, None
+        if debug:
+            dump = {"commitments": np.zeros((self.num_commitments(kinds), count, 32), np.uint8), "status": np.zeros(count, np.uint32)}
+            dbg = B.afx_debug_dump(None, dump["commitments"].ctypes.data, None, dump["status"].ctypes.data)
+        self._b.check(self._b.L.afx_show(self._h, ctypes.byref(cb), ctypes.byref(ob), status.ctypes.data, ctypes.byref(dbg) if dbg is not None else None))
+        res = PresentationBatch(kinds, out)
+        return (res, status, dump) if debug else (res, status)
+
+    def show_batch_device(self, kinds, count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream=0):
+        self._b.check(self._b.L.afx_show_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream))
+
     def issue_batch_device(self, kinds, count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream=0):
         self._b.check(self._b.L.afx_issue_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream))
 

@@ -173,6 +173,21 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     assert int(verdicts_dev.sum().item()) == 0, "issued credentials failed CredentialIssuance::verify"
     out["verify_issuance_4attr"] = {"workload": "batch CredentialIssuance::verify of the %d issuances above" % B,
                                     "value": B / (ms * 1e-3), "unit": "issuances/s", "ms_per_step": ms}
+    # ---- AnonymousCredential::show (user-side prover): inputs = the issuances above as credentials of shape
+    # [PS, PS, PP, PP] (nothing hidden), fresh rng bytes; the presentations are then verified
+    k_show = bytes([0, 0, 2, 2])
+    nf_in, nf_out = 3 + 4 + 2 * (1 + 3), 1 + 3 + 3 + 4 + 4
+    sh = torch.empty((nf_in, B, 32), dtype=torch.uint8, device="cuda")
+    sh[0:3] = iss_dev[n:n + 3]; sh[3:7] = iss_dev[0:4]
+    sh[7:] = torch.from_numpy(rng.integers(0, 256, (nf_in - 7, B, 32), dtype=np.uint8)).cuda()
+    pres_dev = torch.empty((nf_out, B, 32), dtype=torch.uint8, device="cuda")
+    ms = time_device(torch, stream, flush, lambda: issuer4.show_batch_device(k_show, B, sh.data_ptr(), pres_dev.data_ptr(), status_dev.data_ptr(), stream.cuda_stream), steps)
+    assert int(status_dev.sum().item()) == 0
+    issuer4.verify_batch_device(k_show, B, pres_dev.data_ptr(), verdicts_dev.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    assert int(verdicts_dev.sum().item()) == 0, "presentations made on the device failed Issuer::verify"
+    out["show_4attr_revealed"] = {"workload": "batch AnonymousCredential::show of %d all-revealed 4-attribute credentials (user-side prover), verified afterwards" % B,
+                                  "value": B / (ms * 1e-3), "unit": "presentations/s", "ms_per_step": ms}
     # ---- S16 presentations (configs[3]); 16,384 per step keeps the 2.3 GB of ladder tables modest
     try:
         blob = open(os.path.join(ROOT, "bench_data", "issuer16.bin"), "rb").read()

@@ -148,6 +148,27 @@ int afx_issue(afx_ctx* ctx, const afx_request_batch* batch, const afx_issuance_o
 int afx_issue_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
                      void* status_dev, void* stream);
 
+/* Batch AnonymousCredential::show (src/credential.rs:37-46 = ProofOfValidCredential::prove, src/nizk/presentation.rs:139-321, plus
+ * one ProofOfEncryption::prove, src/nizk/encryption.rs:58-142, with Keypair::encrypt, src/symmetric.rs:252-261, per hidden
+ * plaintext attribute).  The USER-side batch operation: it needs no issuer secret, so a context created with
+ * secret = NULL suffices.  As with afx_issue the rng output (z and the blindings) is passed explicitly, 64 bytes per value.
+ *
+ * kinds = the attribute kinds of the presentation to produce (AFX_KIND_*), h_s = #hidden scalars, h_p = #hidden plaintexts.
+ * Input fields:  t, U, V   (the credential's aMAC, src/amacs.rs:248-252),
+ *                per attribute in index order: the scalar m_i (kinds 0, 1) | the point M_i (kind 2; for a revealed plaintext its
+ *                M1) | the plaintext M1, M2, m3 (kind 3; src/symmetric.rs:89-96),
+ *                a, a0, a1, pk of the symmetric keypair (src/symmetric.rs:74-79) -- present only when h_p > 0,
+ *                then (lo, hi) 32-byte halves of the rng bytes of: z, the 3 + h_s blindings of the presentation proof (witness
+ *                order z, z_0, t, m...), and 6 blindings per hidden plaintext (a, a0, a1, m3, z, z1).
+ * Output fields: exactly the presentation layout documented at the top of this header, so the result can be handed to
+ * afx_verify_presentations unchanged.  status: 0 = Ok, 1 = undecodable point / non-canonical scalar in the input (all-zero output). */
+typedef afx_request_batch afx_show_batch;
+typedef afx_issuance_out afx_presentation_out;
+size_t afx_show_num_fields(uint16_t n_attrs, const uint8_t* kinds);
+int afx_show(afx_ctx* ctx, const afx_show_batch* batch, const afx_presentation_out* out, uint8_t* status, afx_debug_dump* dbg);
+int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
+                    void* status_dev, void* stream);
+
 /* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */
 uint64_t afx_launch_count(const afx_ctx* ctx);
 

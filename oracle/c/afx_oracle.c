@@ -521,7 +521,7 @@ API int afxo_make_issuer(uint32_t n, const char* tag, uint8_t* sp_out, uint8_t* 
 typedef struct {
     const afxo_issuer* is; int mode; int n; const uint8_t* kinds; const uint8_t* hide; const char* config;
     uint64_t start, count; int tid, nthreads;
-    const uint8_t* in; uint8_t* out; uint8_t* out2; uint8_t* verdicts; uint8_t* tz; uint8_t* tcommit; uint8_t* tchal; int ncommit_max, nchal_max;
+    const uint8_t* in; uint8_t* out; uint8_t* out2; uint8_t* out3; uint8_t* verdicts; uint8_t* tz; uint8_t* tcommit; uint8_t* tchal; int ncommit_max, nchal_max;
     const uint8_t* randomness; double verify_seconds;
 } job;
 
@@ -569,9 +569,23 @@ static void* worker(void* arg) {
             for (int k = 0; k < n; k++) if (j->hide[k]) { if (at[k].kind == 'S') { at[k].kind = 's'; hs++; } else if (at[k].kind == 'E') { at[k].kind = 'H'; hp++; } }
             keypair_derive(&kp, is, ms);
             uint8_t zs[32], pb[3 + MAXN][32], eb[6 * MAXN][32];
-            rng_scalar(&r, zs);
-            for (int k = 0; k < 3 + hs; k++) rng_scalar(&r, pb[k]);
-            for (int k = 0; k < 6 * hp; k++) rng_scalar(&r, eb[k]);
+            uint8_t seeds[1 + 3 + MAXN + 6 * MAXN][64]; int ns = 0;      /* the rng output behind z and every blinding (Scalar::random = 64 bytes mod l) */
+            rng_fill(&r, seeds[ns], 64); sc_from_wide(zs, seeds[ns++]);
+            for (int k = 0; k < 3 + hs; k++) { rng_fill(&r, seeds[ns], 64); sc_from_wide(pb[k], seeds[ns++]); }
+            for (int k = 0; k < 6 * hp; k++) { rng_fill(&r, seeds[ns], 64); sc_from_wide(eb[k], seeds[ns++]); }
+            if (j->out3) { /* the flat input of a batch AnonymousCredential::show for this item (include/aeonflux_b200.h, afx_show) */
+                int Ws = 3 + 2 * ns + (hp ? 4 : 0); for (int k = 0; k < n; k++) Ws += at[k].kind == 'H' ? 3 : 1;
+                uint8_t(*w)[32] = (uint8_t(*)[32])(j->out3 + i * (uint64_t)Ws * 32); int q = 0;
+                memcpy(w[q++], t, 32); ge_compress(w[q++], &U); ge_compress(w[q++], &V);
+                for (int k = 0; k < n; k++) {
+                    if (at[k].kind == 'S' || at[k].kind == 's') memcpy(w[q++], at[k].sc, 32);
+                    else if (at[k].kind == 'P') ge_compress(w[q++], &at[k].pt);
+                    else if (at[k].kind == 'E') ge_compress(w[q++], &at[k].pl.M1);
+                    else { ge_compress(w[q++], &at[k].pl.M1); ge_compress(w[q++], &at[k].pl.M2); memcpy(w[q++], at[k].pl.m3, 32); }
+                }
+                if (hp) { memcpy(w[q++], kp.a, 32); memcpy(w[q++], kp.a0, 32); memcpy(w[q++], kp.a1, 32); ge_compress(w[q++], &kp.pk); }
+                for (int k = 0; k < ns; k++) { memcpy(w[q++], seeds[k], 32); memcpy(w[q++], seeds[k] + 32, 32); }
+            }
             if (j->out) {
                 presentation_prove(is, at, t, &U, &V, &kp, zs, (const uint8_t(*)[32])pb, (const uint8_t(*)[32])eb, &p);
                 int W = presentation_words(n, p.kinds);
@@ -639,11 +653,11 @@ API double afxo_verify_presentations(const afxo_issuer* is, const uint8_t* kinds
 }
 /* request_kinds: 'S' scalar, 'P' point, 'E' 30-byte plaintext; hide[k] != 0 => hidden at presentation */
 API double afxo_synth(const afxo_issuer* is, const uint8_t* request_kinds, const uint8_t* hide, int n, const char* config, uint64_t start, uint64_t count,
-                      int threads, uint8_t* presentations_out, uint8_t* issuances_out) {
+                      int threads, uint8_t* presentations_out, uint8_t* issuances_out, uint8_t* show_inputs_out) {
     if (!is || !is->has_secret || (uint32_t)n != is->n) return -1;
     job j; memset(&j, 0, sizeof j);
     j.is = is; j.mode = 1; j.n = n; j.kinds = request_kinds; j.hide = hide; j.config = config; j.start = start; j.count = count;
-    j.out = presentations_out; j.out2 = issuances_out;
+    j.out = presentations_out; j.out2 = issuances_out; j.out3 = show_inputs_out;
     double t0 = now_s(); run_jobs(&j, threads); return now_s() - t0;
 }
 API double afxo_verify_issuances(const afxo_issuer* is, const uint8_t* kinds, int n, const uint8_t* items, uint64_t count, int threads,

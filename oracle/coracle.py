@@ -38,7 +38,7 @@ def lib():
         L.afxo_verify_presentations.restype = c_dbl
         L.afxo_verify_presentations.argtypes = [ctypes.c_void_p, u8p, c_int, u8p, c_u64, c_int, u8p, u8p, u8p, c_int, u8p, c_int]
         L.afxo_synth.restype = c_dbl
-        L.afxo_synth.argtypes = [ctypes.c_void_p, u8p, u8p, c_int, ctypes.c_char_p, c_u64, c_u64, c_int, u8p, u8p]
+        L.afxo_synth.argtypes = [ctypes.c_void_p, u8p, u8p, c_int, ctypes.c_char_p, c_u64, c_u64, c_int, u8p, u8p, u8p]
         L.afxo_verify_issuances.restype = c_dbl
         L.afxo_verify_issuances.argtypes = [ctypes.c_void_p, u8p, c_int, u8p, c_u64, c_int, u8p, u8p, u8p]
         L.afxo_issue.restype = c_dbl
@@ -98,9 +98,11 @@ class Issuer:
             lib().afxo_issuer_free(self._h)
             self._h = None
 
-    def synth(self, request_kinds: bytes, hide, config: bytes, start: int, count: int, threads: int = 0, want_issuances=True):
+    def synth(self, request_kinds: bytes, hide, config: bytes, start: int, count: int, threads: int = 0, want_issuances=True,
+              want_show_inputs=False):
         """request_kinds: bytes of b'S' / b'P' / b'E'.  -> (presentation kinds, presentations [count][W][32] u8,
-        issuances [count][Wi][32] u8)"""
+        issuances [count][Wi][32] u8); with want_show_inputs also the flat input of the batch AnonymousCredential::show that
+        produces exactly those presentations ([count][Ws][32]: credential, attributes, keypair, rng bytes)."""
         n = self.n
         assert len(request_kinds) == n
         hide_flags = np.zeros(n, np.uint8)
@@ -119,8 +121,15 @@ class Issuer:
         pres = np.zeros((count, W, 32), np.uint8)
         iss = np.zeros((count, Wi, 32), np.uint8) if want_issuances else None
         rk = _buf(request_kinds)
-        t = lib().afxo_synth(self._h, _p(rk), _p(hide_flags), n, config, start, count, threads or os.cpu_count(), _p(pres), _p(iss))
+        show = None
+        if want_show_inputs:
+            hs, hp = sum(k == KIND_SS for k in kinds), sum(k == KIND_SP for k in kinds)
+            Ws = 3 + sum(3 if k == KIND_SP else 1 for k in kinds) + (4 if hp else 0) + 2 * (1 + 3 + hs + 6 * hp)
+            show = np.zeros((count, Ws, 32), np.uint8)
+        t = lib().afxo_synth(self._h, _p(rk), _p(hide_flags), n, config, start, count, threads or os.cpu_count(), _p(pres), _p(iss), _p(show))
         assert t >= 0
+        if want_show_inputs:
+            return bytes(kinds), pres, iss, show
         return bytes(kinds), pres, iss
 
     def verify_presentations(self, kinds: bytes, items: np.ndarray, threads: int = 0, trace=False):

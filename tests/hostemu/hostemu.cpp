@@ -55,11 +55,11 @@ static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* msms, const u32
     std::vector<u32> scratch((size_t)max_terms * 8);
     for (u32 k = 0; k < nidx; k++) for (u32 i = 0; i < ws.count; i++) msm_ct_job(ws, msms[idx[k]], i, scratch.data(), 1);
 }
-static void be_launch_derive(const Workspace& ws, const WideDesc* d, u32 nd, be_stream) {
-    for (u32 k = 0; k < nd; k++) for (u32 i = 0; i < ws.count; i++) derive_job(ws, d[k], k, i);
+static void be_launch_derive(const Workspace& ws, const DeriveOp* d, u32 nd, be_stream) {
+    for (u32 i = 0; i < ws.count; i++) derive_program_job(ws, d, nd, i);
 }
-static void be_launch_issue_out(const Workspace& ws, const IssueOutDesc* d, u32 nwords, u32* out, be_stream) {
-    for (u32 k = 0; k < nwords; k++) for (u32 i = 0; i < ws.count; i++) issue_out_job(ws, *d, k, i, out);
+static void be_launch_out_words(const Workspace& ws, const OutWord* d, u32 nwords, u32* out, be_stream) {
+    for (u32 k = 0; k < nwords; k++) for (u32 i = 0; i < ws.count; i++) out_word_job(ws, d[k], k, i, out);
 }
 static void be_launch_transcript(const Workspace& ws, const TxDesc* txs, u32 ntx, be_stream) {
     for (u32 k = 0; k < ntx; k++) for (u32 i = 0; i < ws.count; i++) transcript_job(ws, txs[k], i);

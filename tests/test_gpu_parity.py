@@ -268,3 +268,51 @@ def test_multi_chunk_host_call_is_pipelined_and_exact(readme4):
     assert (iss.verify_wire(bytes([0, 0, 2, 2]), issu, issuance=True) == ovi).all()
     big = Issuer(sp, ip, sk, device=0, max_batch=8192)
     assert (big.verify_wire(kinds, pres) == ov).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SHAPES)
+def test_show_golden_shapes(coracle, name):
+    """AnonymousCredential::show on the GPU with supplied rng output: byte-identical to the oracle prover's presentations (item 0
+    is the committed fixture), on a ragged batch over two chunks; the presentations verify like the oracle says."""
+    from aeonflux_b200 import Issuer
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    orc = coracle.Issuer(sp, ip, sk)
+    rk = bytes(REQ[k] for k in g["request"])
+    count = 70
+    kinds, pres, _, showin = orc.synth(rk, g["hide"], g["config"].encode(), 0, count, want_issuances=False, want_show_inputs=True)
+    user = Issuer(sp, ip, None, device=0, max_batch=64)
+    fields = np.ascontiguousarray(showin.transpose(1, 0, 2))
+    fields[0, 9, 31] = 0xff                                     # item 9: t is not a canonical scalar
+    res, st = user.show_batch(kinds, fields)
+    got = res.fields.transpose(1, 0, 2)
+    ok = np.ones(count, bool); ok[9] = False
+    assert st[9] == 1 and not got[9].any() and not st[ok].any()
+    assert (got[ok] == pres[ok]).all()
+    assert got[0].tobytes().hex() == "".join(g["items"][0]["words"])
+    iss = Issuer(sp, ip, sk, device=0, max_batch=64)
+    v = iss.verify_batch(res)
+    ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(got))
+    assert (v == ov).all() and (v[ok] == g["items"][0]["verdict"]).all()
+
+
+def test_show_full_size_round_trip(readme4):
+    """65,536 README-4 presentations made on the device from 2,048 credentials x 32 independent rng draws, then verified on the
+    device: every one is accepted, presentations of the same credential differ (fresh z), a sample equals the oracle prover."""
+    from aeonflux_b200 import Issuer
+    orc, _, (sp, ip, sk) = readme4
+    base = 2048
+    kinds, pres, _, showin = orc.synth(b"SSPE", [0, 3], b"show-full", 0, base, want_issuances=False, want_show_inputs=True)
+    count = 65536
+    fields = np.tile(np.ascontiguousarray(showin.transpose(1, 0, 2)), (1, count // base, 1))
+    nrand = 2 * (1 + 4 + 6)
+    rng = np.random.default_rng(41)
+    fields[-nrand:, base:] = rng.integers(0, 256, (nrand, count - base, 32), dtype=np.uint8)      # fresh z / blindings beyond the first copy
+    user = Issuer(sp, ip, None, device=0, max_batch=count)
+    res, st = user.show_batch(kinds, fields)
+    assert not st.any()
+    got = res.fields.transpose(1, 0, 2)
+    assert (got[:base] == pres).all()
+    assert (got[base:2 * base, 5] != got[:base, 5]).any(axis=1).all()                            # C_x_0 depends on z
+    iss = Issuer(sp, ip, sk, device=0, max_batch=count)
+    assert not iss.verify_batch(res).any()

@@ -128,6 +128,37 @@ def test_issue_stage_logic_matches_golden_and_oracle(emu, coracle, name):
     assert list(iss.verify_issuance_batch(res)) == [0, 0, 0, 1, 0]
 
 
+@pytest.mark.parametrize("name", GOLDEN_SHAPES)
+def test_show_stage_logic_matches_golden_and_oracle(emu, coracle, name):
+    """AnonymousCredential::show (credential.rs:37-46) with supplied rng output: byte-identical to the presentations the oracle's
+    prover makes from the same credential and rng bytes (item 0 = the committed Python-oracle fixture); the result verifies;
+    malformed inputs give status 1 and all-zero words."""
+    from aeonflux_b200 import Issuer
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    orc = coracle.Issuer(sp, ip, sk)
+    rk = bytes(REQ[k] for k in g["request"])
+    kinds, pres, _, showin = orc.synth(rk, g["hide"], g["config"].encode(), 0, 5, want_issuances=False, want_show_inputs=True)
+    assert pres[0].tobytes().hex() == "".join(g["items"][0]["words"])
+    user = Issuer(sp, ip, None, max_batch=3, _binding=emu)          # the user-side context holds no issuer secret
+    fields = np.ascontiguousarray(showin.transpose(1, 0, 2))
+    fields[2, 3, 0] ^= 1                                            # item 3: V no longer decodes (or is another point)
+    res, st, dbg = user.show_batch(kinds, fields, debug=True)
+    got = res.fields.transpose(1, 0, 2)
+    ok = [0, 1, 2, 4]
+    assert (got[ok] == pres[ok]).all()
+    assert got[0].tobytes().hex() == "".join(g["items"][0]["words"])
+    if st[3]:
+        assert not got[3].any()
+    iss = Issuer(sp, ip, sk, max_batch=8, _binding=emu)
+    v = iss.verify_batch(res)
+    ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(got))
+    assert (v == ov).all() and list(v[ok]) == [g["items"][0]["verdict"]] * 4
+    # the prover's blinding commitments are the ones the verifier recomputes
+    _, vdbg = iss.verify_batch(res, debug=True)
+    assert (dbg["commitments"][:, ok] == vdbg["commitments"][:, ok]).all() or g["items"][0]["verdict"] == 1
+
+
 def test_issue_edges(emu, coracle):
     from aeonflux_b200 import Issuer, RequestBatch
     from aeonflux_b200._binding import AfxError
