@@ -117,6 +117,47 @@ def load_fixture(batch):
     return sp, ip, sk, items
 
 
+def synthesize_on_device(torch, issuer, B, seed, stream):
+    """65,536 DISTINCT honest README-4 presentations made on the GPU itself: random attributes -> Issuer::issue (credentials) ->
+    AnonymousCredential::show with attributes 0 and 3 hidden (fresh z and blindings per item, one symmetric keypair).  Returns the
+    device-resident struct-of-arrays batch [28][B][32].  (Needs no CPU oracle; a sample is cross-checked against it afterwards.)"""
+    rng = np.random.default_rng(seed)
+    s = stream.cuda_stream
+
+    def rand_words(k):
+        return torch.from_numpy(rng.integers(0, 256, (k, B, 32), dtype=np.uint8)).cuda()
+
+    def rand_scalars(k):
+        w = rng.integers(0, 256, (k, B, 32), dtype=np.uint8); w[:, :, 31] &= 0x0f       # < 2^252 < l
+        return torch.from_numpy(w).cuda()
+
+    status = torch.empty(B, dtype=torch.uint8, device="cuda")
+    # valid, distinct points: the U = RistrettoPoint::from_uniform_bytes(rng) outputs of three throw-away issuances
+    pts = []
+    for _ in range(3):
+        req = torch.cat([rand_scalars(4), rand_words(22)])
+        out = torch.empty((13, B, 32), dtype=torch.uint8, device="cuda")
+        issuer.issue_batch_device(bytes([0, 0, 0, 0]), B, req.data_ptr(), out.data_ptr(), status.data_ptr(), s)
+        torch.cuda.synchronize()
+        pts.append(out[1].clone())
+    P2, M1, M2 = pts
+    m = rand_scalars(3)                                                                  # m0, m1, m3
+    # credentials over attributes [m0, m1, P2, plaintext(M1, M2, m3)] (the plaintext enters the aMAC through M1, amacs.rs:241)
+    req = torch.cat([m[0:2], P2[None], M1[None], rand_words(22)])
+    cred = torch.empty((13, B, 32), dtype=torch.uint8, device="cuda")
+    issuer.issue_batch_device(bytes([0, 0, 2, 2]), B, req.data_ptr(), cred.data_ptr(), status.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert int(status.sum().item()) == 0
+    kp = np.frombuffer(open(os.path.join(ROOT, "bench_data", "keypair4.bin"), "rb").read(), np.uint8).reshape(4, 1, 32)
+    kp_dev = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(kp, (4, B, 32)))).cuda()
+    show_in = torch.cat([cred[0:3], m[0:2], P2[None], M1[None], M2[None], m[2:3], kp_dev, rand_words(22)])   # 35 fields
+    pres = torch.empty((WORDS, B, 32), dtype=torch.uint8, device="cuda")
+    issuer.show_batch_device(KINDS_README4, B, show_in.data_ptr(), pres.data_ptr(), status.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert int(status.sum().item()) == 0
+    return pres
+
+
 def cpu_leg(sp, ip, sk, items, sample, threads):
     """The restated reference CPU path (oracle/c, reference schedule) on `sample` items with `threads` host threads."""
     from oracle import coracle as C
@@ -244,6 +285,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the issuance / S16 measurements (configs[2], configs[3])")
+    ap.add_argument("--tiled-input", action="store_true", help="tile the 1,024-item CPU-made fixture instead of synthesizing the batch on the device")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -265,8 +307,16 @@ def main():
     issuer = Issuer(sp, ip, sk, device=local, max_batch=B)
     # host staging in pinned memory (the e2e leg copies from here); SoA [field][item][32]
     host = torch.empty((WORDS, B, 32), dtype=torch.uint8).pin_memory()
-    host.numpy()[:] = items.transpose(1, 0, 2)
-    fields_dev = host.cuda(non_blocking=False)
+    if args.tiled_input:
+        host.numpy()[:] = items.transpose(1, 0, 2)
+        fields_dev = host.cuda(non_blocking=False)
+        input_note = "1,024 distinct presentations tiled to the batch (bench_data/make_fixture.py)"
+    else:
+        fields_dev = synthesize_on_device(torch, issuer, B, 1000 + rank, torch.cuda.current_stream())
+        host.copy_(fields_dev)
+        items = np.ascontiguousarray(host.numpy().transpose(1, 0, 2))
+        input_note = "%d distinct presentations per GPU, issued and shown on the device from random attributes (afx_issue -> afx_show); " \
+                     "a sample is cross-checked against the CPU oracle" % B
     verdicts_dev = torch.empty(B, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -380,7 +430,7 @@ def main():
             "data": "synthetic", "config": {"workload": "batch Issuer::verify of 65,536 README-4 presentations [SS,PS,PP,SP] per GPU (BASELINE configs[1])",
                                             "batch_per_gpu": B, "kinds": list(kinds), "bytes_per_item": WORDS * 32,
                                             "l2": "256 MiB flush write between timed steps; 1.2 GB workspace per step exceeds L2",
-                                            "input": "1,024 distinct presentations tiled to the batch (bench_data/make_fixture.py)"},
+                                            "input": input_note},
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "presentations/s", "h2d_bytes_per_step": B * WORDS * 32, "d2h_bytes_per_step": B, "ms_per_step": e2e_ms_max / args.steps,
                     "api": "afx_verify_presentations_wire: item-major bytes in pinned host memory -> verdict bytes in host memory",

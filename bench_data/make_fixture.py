@@ -23,6 +23,10 @@ pres.tofile(os.path.join(HERE, "readme4_1024.bin"))
 open(os.path.join(HERE, "issuer4.bin"), "wb").write(sp + ip + sk)
 print("wrote", pres.shape, len(sp), len(ip), len(sk))
 
+# one symmetric keypair for the README-4 issuer (a, a0, a1, pk), used by bench.py when it synthesizes presentations on the device
+from oracle.pyoracle import aeonflux as A, ristretto as R  # noqa: E402
+kp = A.SymmetricKeypair.derive(b"aeonflux-b200 bench keypair".ljust(64, b"\0"), A.SystemParameters.from_bytes(sp))
+open(os.path.join(HERE, "keypair4.bin"), "wb").write(R.sc_to_bytes(kp.a) + R.sc_to_bytes(kp.a0) + R.sc_to_bytes(kp.a1) + kp.pk.compress())
 sp, ip, sk = C.make_issuer(16)
 iss = C.Issuer(sp, ip, sk)
 kinds, pres, _ = iss.synth(b"SSSSSSPP" + b"E" * 8, [0, 1] + list(range(8, 16)), b"bench-s16", 0, 256, want_issuances=False)
