@@ -229,14 +229,14 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     assert int(verdicts_dev.sum().item()) == 0, "presentations made on the device failed Issuer::verify"
     out["show_4attr_revealed"] = {"workload": "batch AnonymousCredential::show of %d all-revealed 4-attribute credentials (user-side prover), verified afterwards" % B,
                                   "value": B / (ms * 1e-3), "unit": "presentations/s", "ms_per_step": ms}
-    # ---- S16 presentations (configs[3]); 16,384 per step keeps the 2.3 GB of ladder tables modest
+    # ---- S16 presentations (configs[3]) at the config's full batch: 65,536 x 4,576 B in, 4.6 GB of ladder tables
     try:
         blob = open(os.path.join(ROOT, "bench_data", "issuer16.bin"), "rb").read()
         pres = np.fromfile(os.path.join(ROOT, "bench_data", "s16_256.bin"), np.uint8).reshape(-1, 143, 32)
     except OSError:
         return out
     sp, ip, sk = blob[:1316], blob[1316:1380], blob[1380:]
-    B16 = min(B, 16384)
+    B16 = B
     k16 = bytes([1, 1, 0, 0, 0, 0, 2, 2] + [3] * 8)
     issuer16 = Issuer(sp, ip, sk, device=local, max_batch=B16)
     f16 = torch.from_numpy(np.ascontiguousarray(np.tile(pres, ((B16 + 255) // 256, 1, 1))[:B16].transpose(1, 0, 2))).cuda()
