@@ -203,6 +203,17 @@ static void be_launch_scalar_check(const Workspace& ws, const u16* d_fields, u32
 static void be_launch_points(const Workspace& ws, const PointJob* d_jobs, u32 njobs, be_stream s) {
     k_points<<<grid_for(ws.count, TPB, njobs), TPB, 0, s>>>(ws, d_jobs);
 }
+// The opt-in to > 48 KiB of dynamic shared memory is a per-device function attribute: set it once per (kernel, device).
+static void allow_large_smem(const void* kernel, int which) {
+    static bool done[2][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !done[which][dev]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (dev >= 0 && dev < 64) done[which][dev] = true;
+    }
+}
+
 // One launch for the aMAC ladder (if `amac`) plus the MSMs of one scratch-size group.
 // The last n_dep_jobs entries of d_idx are the MSMs that wait on the aMAC flags.
 static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac_nps, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 n_dep_jobs,
@@ -216,8 +227,7 @@ static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac
         smem = (size_t)terms * 8 * tpb * 4 + (size_t)nstage * CTAB_ENTRIES * 96;
         if (smem <= LADDER_SMEM_BUDGET || tpb <= 32) break;
     }
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_ladders, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
+    allow_large_smem((const void*)k_ladders, 0);
     const u32 nx = (ws.count + tpb - 1) / tpb;
     const u32 n_dep = n_dep_jobs < nidx ? n_dep_jobs : nidx, n_ind = nidx - n_dep;
     const u32 head = n_ind * nx + (amac ? nx : 0);
@@ -234,8 +244,7 @@ static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* d_msms, const u
         smem = (size_t)max_terms * 8 * tpb * 4;
         if (smem <= LADDER_SMEM_BUDGET || tpb <= 32) break;
     }
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_msm_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
+    allow_large_smem((const void*)k_msm_ct, 1);
     k_msm_ct<<<grid_for(ws.count, tpb, nidx), tpb, smem, s>>>(ws, d_msms, d_idx);
 }
 static void be_launch_derive(const Workspace& ws, const DeriveOp* d, u32 nd, be_stream s) {

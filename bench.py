@@ -310,7 +310,7 @@ def main():
     if args.tiled_input:
         host.numpy()[:] = items.transpose(1, 0, 2)
         fields_dev = host.cuda(non_blocking=False)
-        input_note = "1,024 distinct presentations tiled to the batch (bench_data/make_fixture.py)"
+        input_note = "1,024 distinct presentations tiled to the batch (tests/golden/make_bench_fixture.py)"
     else:
         fields_dev = synthesize_on_device(torch, issuer, B, 1000 + rank, torch.cuda.current_stream())
         host.copy_(fields_dev)

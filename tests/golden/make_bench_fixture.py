@@ -5,14 +5,15 @@ bench.py tiles these to the 65,536-item batch of BASELINE config 2: every item i
 is data-independent, so tiling changes neither the work nor the memory traffic (each item still owns its own workspace rows).
 Also writes bench_data/s16_256.bin / issuer16.bin: 256 honest S16 presentations (kinds [SS,SS,PS,PS,PS,PS,PP,PP,SPx8], 143 words,
 BASELINE config 4) for bench.py's secondary measurements.
-Run from the repo root:  python bench_data/make_fixture.py"""
+Run from the repo root:  python tests/golden/make_bench_fixture.py   (test infrastructure: it uses the oracle; bench.py only reads the files)"""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 from oracle import coracle as C  # noqa: E402
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(ROOT, "bench_data")
 sp, ip, sk = C.make_issuer(4)
 iss = C.Issuer(sp, ip, sk)
 kinds, pres, _ = iss.synth(b"SSPE", [0, 3], b"bench-readme4", 0, 1024, want_issuances=False)

@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Small run of every batch operation for compute-sanitizer (memcheck / racecheck / synccheck):
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from aeonflux_b200 import Issuer, PresentationBatch, RequestBatch  # noqa: E402
 from oracle import coracle as C  # noqa: E402

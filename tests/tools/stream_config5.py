@@ -2,8 +2,8 @@
 """BASELINE configs[4]: streamed verification of N mixed presentations (50 % README-4, 50 % S16, 1 % corrupted), bucketed by
 shape into chunks of 65,536 and sharded over the ranks of the process group (contiguous slices, verdict bitmap gathered).
 
-    python tools/stream_config5.py [--items 4194304] [--chunk 65536]
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tools/stream_config5.py ...
+    python tests/tools/stream_config5.py [--items 4194304] [--chunk 65536]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tests/tools/stream_config5.py ...
 
 Inputs are tiled from the committed bench fixtures (every item is independent, so tiling changes neither work nor traffic);
 corruption = one flipped bit in a random word, which every verdict must catch (every word of a presentation is bound by a
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 K4 = bytes([1, 0, 2, 3])
