@@ -1,5 +1,5 @@
 #!/bin/bash
-# dev helper: time prebuilt library variants gpurun_variants_<name>.so with the short bench (stage times only)
+# dev helper: time prebuilt library variants gpurun_variants_<name>.so with the short bench (stage times only) and check parity
 mkdir -p gpurun_out
 for f in gpurun_variants_*.so; do
   name=${f#gpurun_variants_}; name=${name%.so}
@@ -14,4 +14,5 @@ try:
 except Exception as e:
     print(name, "failed", e)
 PY
+  if [ "$1" == "test" ]; then timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "golden_shapes or readme4_batch" 2>&1 | tail -2; fi
 done
