@@ -30,7 +30,7 @@ class AfxError(RuntimeError):
 class Binding:
     SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
                "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
-               "afx_verify_issuances_device", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
+               "afx_verify_issuances_device", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -65,6 +65,8 @@ class Binding:
         L.afx_show.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), ctypes.POINTER(afx_issuance_out), vp, ctypes.POINTER(afx_debug_dump)]
         L.afx_show_device.restype = ctypes.c_int
         L.afx_show_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp, vp]
+        L.afx_selftest_primitive.restype = ctypes.c_int
+        L.afx_selftest_primitive.argtypes = [vp, ctypes.c_int, vp, sz, vp, vp]
         L.afx_launch_count.restype = ctypes.c_uint64
         L.afx_launch_count.argtypes = [vp]
         L.afx_set_stage_timing.restype = None

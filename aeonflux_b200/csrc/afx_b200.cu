@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(128) k_comb_setup(const u32* enc, u32 ncp, u32
     u32 b = t / (COMB_WINDOWS * COMB_ENTRIES), r = t % (COMB_WINDOWS * COMB_ENTRIES);
     comb_entry_job(enc + 8 * b, r / COMB_ENTRIES, r % COMB_ENTRIES + 1, comb + (size_t)t * 24);
 }
+__global__ void __launch_bounds__(128) k_primitive(u32 op, const u32* in, u32* out, u32* flags, u32 count) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < count) primitive_job(op, in, out, flags, item);
+}
 __global__ void k_secret_setup(const u32* secsc, u32 nsec, u32* secdig, const u32* Wenc, u32* W_pniels, u32* bad) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nsec) {
@@ -266,6 +270,9 @@ static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d
 static void be_launch_comb_setup(const u32* d_enc, u32 ncp, u32* d_comb, be_stream s) {
     u32 total = ncp * COMB_WINDOWS * COMB_ENTRIES;
     k_comb_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_comb);
+}
+static void be_launch_primitive(u32 op, const u32* in, u32* out, u32* flags, u32 count, be_stream s) {
+    k_primitive<<<(count + 127) / 128, 128, 0, s>>>(op, in, out, flags, count);
 }
 static void be_launch_secret_setup(const u32* d_secsc, u32 nsec, u32* d_secdig, const u32* d_Wenc, u32* d_W, u32* d_bad, be_stream s) {
     k_secret_setup<<<1, 64, 0, s>>>(d_secsc, nsec, d_secdig, d_Wenc, d_W, d_bad);

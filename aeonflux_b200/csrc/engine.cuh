@@ -611,6 +611,48 @@ AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words
     return ok;
 }
 
+// ---- primitive self-test (parity hooks for the field / group / scalar code, independent of the protocol flows) ------
+enum : u32 { PRIM_DECOMPRESS_COMPRESS = 0, PRIM_FROM_UNIFORM = 1, PRIM_SCALARMULT = 2, PRIM_WIDE_REDUCE = 3, PRIM_SC_MULADD = 4 };
+// in/out are [count][words][8] item-major.  Returns per item ok (1) / rejected encoding (0) in flags.
+//   0: in 1 word (encoding)          -> out 1 word: compress(decompress(in)); flag = decodes
+//   1: in 2 words (64 uniform bytes) -> out 1 word: compress(from_uniform_bytes(in))
+//   2: in 2 words (scalar, encoding) -> out 1 word: compress(scalar * point)  (fixed-window ladder over the [1P..8P] table)
+//   3: in 2 words (64 bytes)         -> out 1 word: the integer mod l
+//   4: in 3 words (a, b, c)          -> out 1 word: a*b + c mod l
+AFX_HD void primitive_job(u32 op, const u32* in, u32* out, u32* flags, u32 item) {
+    u32 w[8]; u32 ok = 1;
+    if (op == PRIM_DECOMPRESS_COMPRESS) {
+        ge p; ok = ge_decompress(p, in + (size_t)item * 8);
+        ge_compress(w, p);
+    } else if (op == PRIM_FROM_UNIFORM) {
+        ge_compress(w, ge_from_uniform(in + (size_t)item * 16));
+    } else if (op == PRIM_SCALARMULT) {
+        ge p; ok = ge_decompress(p, in + (size_t)item * 16 + 8);
+        sc s = sc_from_words(in + (size_t)item * 16);
+        ok &= sc_is_canonical(s);
+        u32 rec[8]; sc_recode16(rec, s);
+        pniels tab[8];
+        struct Keep { pniels* t; AFX_HD void operator()(int e, const pniels& n) const { t[e] = n; } };
+        Keep keep{tab}; ge_table8(p, keep);
+        ge acc = ge_identity();
+        for (int i = 63; i >= 0; i--) {
+            if (i != 63) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
+            int dig = sc_digit16(rec, i);
+            if (dig != 0) { u32 mag = (u32)(dig < 0 ? -dig : dig); acc = ge_add_pn(acc, pniels_cneg(tab[mag - 1], (u32)dig >> 31), true); }
+        }
+        ge_compress(w, acc);
+    } else if (op == PRIM_WIDE_REDUCE) {
+        sc r = sc_reduce512(in + (size_t)item * 16);
+        for (int i = 0; i < 8; i++) w[i] = r.v[i];
+    } else {
+        const u32* q = in + (size_t)item * 24;
+        sc r = sc_muladd(sc_from_words(q), sc_from_words(q + 8), sc_from_words(q + 16));
+        for (int i = 0; i < 8; i++) w[i] = r.v[i];
+    }
+    for (int i = 0; i < 8; i++) out[(size_t)item * 8 + i] = w[i];
+    flags[item] = ok;
+}
+
 // entry (base b, window i, multiple e in 1..8) of the radix-16 comb: (e * 16^i) * P in affine Niels form.
 AFX_HD void comb_entry_job(const u32* enc /*8 words*/, u32 i, u32 e, u32* out /*24 words*/) {
     ge p; ge_decompress(p, enc);

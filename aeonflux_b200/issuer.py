@@ -227,6 +227,17 @@ class Issuer:
     def verify_issuance_batch_device(self, kinds, count, fields_dev_ptr, verdicts_dev_ptr, stream=0):
         self._b.check(self._b.L.afx_verify_issuances_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, verdicts_dev_ptr, stream))
 
+    PRIMITIVES = {"decompress_compress": (0, 32), "from_uniform": (1, 64), "scalarmult": (2, 64), "wide_reduce": (3, 64), "sc_muladd": (4, 96)}
+
+    def selftest_primitive(self, name, inputs):
+        """Run one field/group/scalar primitive of the engine over raw inputs (uint8 [count][in_bytes]) -> (out [count][32], ok [count])."""
+        op, width = self.PRIMITIVES[name]
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8).reshape(-1, width)
+        out = np.zeros((inputs.shape[0], 32), np.uint8)
+        ok = np.zeros(inputs.shape[0], np.uint8)
+        self._b.check(self._b.L.afx_selftest_primitive(self._h, op, inputs.ctypes.data, inputs.shape[0], out.ctypes.data, ok.ctypes.data))
+        return out, ok
+
     def verify_batch_device(self, kinds, count, fields_dev_ptr, verdicts_dev_ptr, stream=0):
         """Enqueue Issuer::verify for a batch already in device memory ([n_fields][count][32]); no synchronisation."""
         self._b.check(self._b.L.afx_verify_presentations_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, verdicts_dev_ptr, stream))

@@ -169,6 +169,15 @@ int afx_show(afx_ctx* ctx, const afx_show_batch* batch, const afx_presentation_o
 int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
                     void* status_dev, void* stream);
 
+/* Primitive self-test (parity hooks for the field / group / scalar code, independent of the protocol flows).  `in` is
+ * item-major, `out` is [count][32], ok[i] = 1 unless an input encoding was rejected.
+ *   op 0: in [count][32] encoding               -> compress(decompress(in))           (CompressedRistretto::decompress / compress)
+ *   op 1: in [count][64] uniform bytes          -> compress(from_uniform_bytes(in))   (RistrettoPoint::from_uniform_bytes)
+ *   op 2: in [count][2][32] scalar, encoding    -> compress(scalar * point)
+ *   op 3: in [count][64] bytes                  -> the integer mod l                  (Scalar::from_bytes_mod_order_wide)
+ *   op 4: in [count][3][32] scalars a, b, c     -> a*b + c mod l */
+int afx_selftest_primitive(afx_ctx* ctx, int op, const uint8_t* in, size_t count, uint8_t* out, uint8_t* ok);
+
 /* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */
 uint64_t afx_launch_count(const afx_ctx* ctx);
 

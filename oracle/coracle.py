@@ -43,6 +43,11 @@ def lib():
         L.afxo_verify_issuances.argtypes = [ctypes.c_void_p, u8p, c_int, u8p, c_u64, c_int, u8p, u8p, u8p]
         L.afxo_issue.restype = c_dbl
         L.afxo_issue.argtypes = [ctypes.c_void_p, u8p, c_int, u8p, u8p, c_u64, c_int, u8p, u8p]
+        L.afxo_decompress_compress.argtypes = [u8p, u8p]
+        L.afxo_from_uniform.argtypes = [u8p, u8p]
+        L.afxo_scalarmult.argtypes = [u8p, u8p, u8p, c_int]
+        L.afxo_sc_from_wide.argtypes = [u8p, u8p]
+        L.afxo_sc_muladd.argtypes = [u8p, u8p, u8p, u8p]
         L.afxo_sysparams_size.argtypes = [ctypes.c_uint32]
         L.afxo_secret_size.argtypes = [ctypes.c_uint32]
         _lib = L

@@ -96,6 +96,9 @@ static void be_launch_comb_setup(const u32* enc, u32 ncp, u32* comb, be_stream) 
         }
     }
 }
+static void be_launch_primitive(u32 op, const u32* in, u32* out, u32* flags, u32 count, be_stream) {
+    for (u32 i = 0; i < count; i++) primitive_job(op, in, out, flags, i);
+}
 static void be_launch_secret_setup(const u32* secsc, u32 nsec, u32* secdig, const u32* Wenc, u32* W, u32* bad, be_stream) {
     for (u32 t = 0; t < nsec; t++) { sc s = sc_from_words(secsc + 8 * t); if (!sc_is_canonical(s)) *bad |= 2; sc_recode16(secdig + 8 * t, s); }
     ge p; if (!ge_decompress(p, Wenc)) *bad |= 1;

@@ -316,3 +316,21 @@ def test_show_full_size_round_trip(readme4):
     assert (got[base:2 * base, 5] != got[:base, 5]).any(axis=1).all()                            # C_x_0 depends on z
     iss = Issuer(sp, ip, sk, device=0, max_batch=count)
     assert not iss.verify_batch(res).any()
+
+
+def test_primitives_on_gpu(coracle):
+    """Field / group / scalar primitives of the CUDA engine against the committed primitive vectors and the C oracle."""
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_primitives
+    sp, ip, sk = coracle.make_issuer(1)
+    iss = Issuer(sp, ip, None, device=0, max_batch=4)
+    check_primitives(iss, coracle)
+    # 20,000 random 32-byte strings: the decode verdicts equal the oracle's (about 6.8 % decode), valid ones round-trip
+    rng = np.random.default_rng(18)
+    enc = rng.integers(0, 256, (20000, 32), dtype=np.uint8)
+    out, ok = iss.selftest_primitive("decompress_compress", enc)
+    L = coracle.lib()
+    scratch = np.zeros(32, np.uint8)
+    exp_ok = np.array([L.afxo_decompress_compress(enc[i].ctypes.data, scratch.ctypes.data) for i in range(20000)], np.uint8)
+    assert (ok == exp_ok).all() and 1000 < ok.sum() < 1800
+    assert (out[ok == 1] == enc[ok == 1]).all()

@@ -252,3 +252,54 @@ def test_key_material_layouts_round_trip(emu, coracle):
         wire.split_secret_key(bytes(nc))
     with pytest.raises(ValueError):
         wire.issuer_from_bytes(blob[:-1])
+
+
+def check_primitives(iss, coracle):
+    """The engine's field / group / scalar primitives against the committed primitive vectors (tests/golden/prims.json, from the
+    Python oracle, itself pinned to libsodium and RFC 9496) and, on random inputs, against the C oracle's hooks."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "prims.json")))
+    L = coracle.lib()
+    hx = lambda rows, k: np.frombuffer(b"".join(bytes.fromhex(r[k]) for r in rows), np.uint8)
+    # decompress validity + round trip, incl. the identity, non-canonical and negative encodings
+    enc = hx(g["decompress"], "in").reshape(-1, 32)
+    extra = np.zeros((4, 32), np.uint8); extra[1, 0] = 1; extra[2] = 0xff; extra[3, :] = 0xed; extra[3, 31] = 0x7f   # 0 (identity), 1 (negative), 2^256-1, p
+    enc = np.concatenate([enc, extra])
+    out, ok = iss.selftest_primitive("decompress_compress", enc)
+    assert list(ok[:64]) == [int(r["valid"]) for r in g["decompress"]] and list(ok[64:]) == [1, 0, 0, 0]
+    assert (out[ok == 1] == enc[ok == 1]).all()                      # compress(decompress(x)) == x for every valid encoding
+    out, ok = iss.selftest_primitive("from_uniform", hx(g["from_uniform"], "in").reshape(-1, 64))
+    assert out.tobytes() == hx(g["from_uniform"], "out").tobytes()
+    sm = np.concatenate([hx(g["scalarmult"], "s").reshape(-1, 32), hx(g["scalarmult"], "p").reshape(-1, 32)], axis=1)
+    out, ok = iss.selftest_primitive("scalarmult", sm)
+    assert ok.all() and out.tobytes() == hx(g["scalarmult"], "out").tobytes()
+    out, ok = iss.selftest_primitive("wide_reduce", hx(g["wide_reduce"], "in").reshape(-1, 64))
+    assert out.tobytes() == hx(g["wide_reduce"], "out").tobytes()
+    # random inputs against the C oracle: edge scalars (0, 1, l-1) times a point, wide reductions of extreme values, a*b+c
+    rng = np.random.default_rng(17)
+    Lm1 = (2**252 + 27742317777372353535851937790883648493 - 1).to_bytes(32, "little")
+    pts = out_pts = iss.selftest_primitive("from_uniform", rng.integers(0, 256, (40, 64), dtype=np.uint8))[0]
+    scal = rng.integers(0, 256, (40, 32), dtype=np.uint8); scal[:, 31] &= 0x0f
+    scal[0] = 0; scal[1] = 0; scal[1, 0] = 1; scal[2] = np.frombuffer(Lm1, np.uint8)
+    got, ok = iss.selftest_primitive("scalarmult", np.concatenate([scal, pts], axis=1))
+    for i in range(40):
+        exp = np.zeros(32, np.uint8)
+        assert L.afxo_scalarmult(scal[i].ctypes.data, pts[i].ctypes.data, exp.ctypes.data, 0) == 1
+        assert (got[i] == exp).all(), i
+    wide = rng.integers(0, 256, (20, 64), dtype=np.uint8); wide[0] = 0xff; wide[1] = 0
+    got, _ = iss.selftest_primitive("wide_reduce", wide)
+    abc = rng.integers(0, 256, (20, 96), dtype=np.uint8); abc[:, 31] &= 0x0f; abc[:, 63] &= 0x0f; abc[:, 95] &= 0x0f
+    abc[0, :32] = np.frombuffer(Lm1, np.uint8); abc[0, 32:64] = np.frombuffer(Lm1, np.uint8); abc[0, 64:] = np.frombuffer(Lm1, np.uint8)
+    got2, _ = iss.selftest_primitive("sc_muladd", abc)
+    for i in range(20):
+        exp = np.zeros(32, np.uint8)
+        L.afxo_sc_from_wide(wide[i].ctypes.data, exp.ctypes.data)
+        assert (got[i] == exp).all()
+        L.afxo_sc_muladd(abc[i, :32].ctypes.data, abc[i, 32:64].ctypes.data, abc[i, 64:].ctypes.data, exp.ctypes.data)
+        assert (got2[i] == exp).all()
+
+
+def test_primitives_on_emulation(emu, coracle):
+    from aeonflux_b200 import Issuer
+    sp, ip, sk = coracle.make_issuer(1)
+    check_primitives(Issuer(sp, ip, None, max_batch=4, _binding=emu), coracle)
