@@ -1,0 +1,174 @@
+//! FFI to `libaeonflux_b200.so` (include/aeonflux_b200.h) and a safe wrapper over byte slices.
+//!
+//! Not compiled in this repository's image (no Rust toolchain); see rust/README.md.  Everything is expressed over the
+//! reference's own byte encodings: `SystemParameters::to_bytes()` (src/parameters.rs:155-184), the 64 bytes `C_W || I`
+//! (src/issuer.rs:155,163), `amacs::SecretKey::to_bytes()` (src/amacs.rs:110-125), canonical scalars and compressed points.
+
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct afx_ctx {
+    _private: [u8; 0],
+}
+
+/// `afx_presentation_batch`, `afx_issuance_batch`, `afx_request_batch` and `afx_show_batch` share this layout.
+#[repr(C)]
+pub struct afx_batch {
+    pub n_attrs: u16,
+    pub kinds: *const u8,
+    pub count: usize,
+    pub fields: *const *const u8,
+    pub n_fields: usize,
+}
+
+/// `afx_issuance_out` / `afx_presentation_out`.
+#[repr(C)]
+pub struct afx_out {
+    pub fields: *const *mut u8,
+    pub n_fields: usize,
+}
+
+#[repr(C)]
+pub struct afx_debug_dump {
+    pub z: *mut u8,
+    pub commitments: *mut u8,
+    pub challenges: *mut u8,
+    pub status: *mut u32,
+}
+
+extern "C" {
+    pub fn afx_ctx_create(sysparams: *const u8, sysparams_len: usize, issuer_pub: *const u8, secret: *const u8, secret_len: usize,
+                          device: c_int, max_batch: usize, out: *mut *mut afx_ctx) -> c_int;
+    pub fn afx_ctx_destroy(ctx: *mut afx_ctx);
+    pub fn afx_presentation_num_fields(n_attrs: u16, kinds: *const u8) -> usize;
+    pub fn afx_request_num_fields(n_attrs: u16) -> usize;
+    pub fn afx_show_num_fields(n_attrs: u16, kinds: *const u8) -> usize;
+    pub fn afx_verify_presentations(ctx: *mut afx_ctx, batch: *const afx_batch, verdicts: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
+    pub fn afx_verify_presentations_wire(ctx: *mut afx_ctx, n_attrs: u16, kinds: *const u8, count: usize, items: *const u8,
+                                         verdicts: *mut u8) -> c_int;
+    pub fn afx_verify_issuances(ctx: *mut afx_ctx, batch: *const afx_batch, verdicts: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
+    pub fn afx_verify_issuances_wire(ctx: *mut afx_ctx, n_attrs: u16, kinds: *const u8, count: usize, items: *const u8,
+                                     verdicts: *mut u8) -> c_int;
+    pub fn afx_issue(ctx: *mut afx_ctx, batch: *const afx_batch, out: *const afx_out, status: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
+    pub fn afx_show(ctx: *mut afx_ctx, batch: *const afx_batch, out: *const afx_out, status: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
+    pub fn afx_strerror(code: c_int) -> *const c_char;
+}
+
+/// A non-zero return code of the C ABI (`AFX_ERR_*`).
+#[derive(Clone, Copy, Debug, Eq, PartialEq)]
+pub struct B200Error(pub i32);
+
+impl std::fmt::Display for B200Error {
+    fn fmt(&self, f: &mut std::fmt::Formatter) -> std::fmt::Result {
+        let msg = unsafe { std::ffi::CStr::from_ptr(afx_strerror(self.0)) };
+        write!(f, "aeonflux_b200 error {}: {}", self.0, msg.to_string_lossy())
+    }
+}
+
+/// One issuer context on one B200.  Replicate it per GPU; every item of a batch is independent.
+pub struct B200Context {
+    ctx: *mut afx_ctx,
+}
+
+// One thread at a time per context (it owns one set of CUDA streams and one workspace).
+unsafe impl Send for B200Context {}
+
+impl B200Context {
+    /// `secret_key = None` gives a user-side context: `verify_issuances*` and `show` work, `verify_presentations*` and `issue` do not.
+    pub fn new(system_parameters: &[u8], issuer_parameters: &[u8; 64], secret_key: Option<&[u8]>, device: i32, max_batch: usize)
+        -> Result<B200Context, B200Error>
+    {
+        let mut ctx: *mut afx_ctx = std::ptr::null_mut();
+        let (sk, sk_len) = match secret_key { Some(s) => (s.as_ptr(), s.len()), None => (std::ptr::null(), 0) };
+        let rc = unsafe {
+            afx_ctx_create(system_parameters.as_ptr(), system_parameters.len(), issuer_parameters.as_ptr(), sk, sk_len,
+                           device as c_int, max_batch, &mut ctx)
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(B200Context { ctx })
+    }
+
+    fn check_fields(fields: &[&[u8]], expected: usize) -> Result<usize, B200Error> {
+        if fields.len() != expected { return Err(B200Error(-1)); }
+        let count = if fields.is_empty() { 0 } else { fields[0].len() / 32 };
+        if fields.iter().any(|f| f.len() != count * 32) { return Err(B200Error(-1)); }
+        Ok(count)
+    }
+
+    /// Batch `Issuer::verify` over struct-of-arrays fields: verdict 0 = `Ok(())`, 1 = `Err(VerificationFailure)`.
+    pub fn verify_presentations(&self, kinds: &[u8], fields: &[&[u8]]) -> Result<Vec<u8>, B200Error> {
+        let n_fields = unsafe { afx_presentation_num_fields(kinds.len() as u16, kinds.as_ptr()) };
+        let count = Self::check_fields(fields, n_fields)?;
+        let ptrs: Vec<*const u8> = fields.iter().map(|f| f.as_ptr()).collect();
+        let batch = afx_batch { n_attrs: kinds.len() as u16, kinds: kinds.as_ptr(), count, fields: ptrs.as_ptr(), n_fields };
+        let mut verdicts = vec![0u8; count];
+        let rc = unsafe { afx_verify_presentations(self.ctx, &batch, verdicts.as_mut_ptr(), std::ptr::null_mut()) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(verdicts)
+    }
+
+    /// Batch `Issuer::verify` over item-major wire bytes (`count * n_fields * 32` bytes, as received).
+    pub fn verify_presentations_wire(&self, kinds: &[u8], items: &[u8]) -> Result<Vec<u8>, B200Error> {
+        let n_fields = unsafe { afx_presentation_num_fields(kinds.len() as u16, kinds.as_ptr()) };
+        if n_fields == 0 || items.len() % (n_fields * 32) != 0 { return Err(B200Error(-1)); }
+        let count = items.len() / (n_fields * 32);
+        let mut verdicts = vec![0u8; count];
+        let rc = unsafe {
+            afx_verify_presentations_wire(self.ctx, kinds.len() as u16, kinds.as_ptr(), count, items.as_ptr(), verdicts.as_mut_ptr())
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(verdicts)
+    }
+
+    /// Batch `CredentialIssuance::verify` over struct-of-arrays fields (`attribute[n], t, U, V, challenge, responses[n+5]`).
+    pub fn verify_issuances(&self, kinds: &[u8], fields: &[&[u8]]) -> Result<Vec<u8>, B200Error> {
+        let n_fields = 2 * kinds.len() + 9;
+        let count = Self::check_fields(fields, n_fields)?;
+        let ptrs: Vec<*const u8> = fields.iter().map(|f| f.as_ptr()).collect();
+        let batch = afx_batch { n_attrs: kinds.len() as u16, kinds: kinds.as_ptr(), count, fields: ptrs.as_ptr(), n_fields };
+        let mut verdicts = vec![0u8; count];
+        let rc = unsafe { afx_verify_issuances(self.ctx, &batch, verdicts.as_mut_ptr(), std::ptr::null_mut()) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(verdicts)
+    }
+
+    fn prove(&self, issue: bool, kinds: &[u8], fields: &[&[u8]], n_in: usize, n_out: usize) -> Result<(Vec<Vec<u8>>, Vec<u8>), B200Error> {
+        let count = Self::check_fields(fields, n_in)?;
+        let ptrs: Vec<*const u8> = fields.iter().map(|f| f.as_ptr()).collect();
+        let batch = afx_batch { n_attrs: kinds.len() as u16, kinds: kinds.as_ptr(), count, fields: ptrs.as_ptr(), n_fields: n_in };
+        let mut out: Vec<Vec<u8>> = vec![vec![0u8; 32 * count]; n_out];
+        let out_ptrs: Vec<*mut u8> = out.iter_mut().map(|f| f.as_mut_ptr()).collect();
+        let out_desc = afx_out { fields: out_ptrs.as_ptr(), n_fields: n_out };
+        let mut status = vec![0u8; count];
+        let rc = unsafe {
+            if issue { afx_issue(self.ctx, &batch, &out_desc, status.as_mut_ptr(), std::ptr::null_mut()) }
+            else { afx_show(self.ctx, &batch, &out_desc, status.as_mut_ptr(), std::ptr::null_mut()) }
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok((out, status))
+    }
+
+    /// Batch `Issuer::issue`: fields = `attribute[n]` then the (lo, hi) halves of the 64 rng bytes of `t`, `U` and the `n+5`
+    /// blindings.  Returns the output words `t, U, V, challenge, responses[n+5]` and a status byte per request.
+    pub fn issue(&self, kinds: &[u8], fields: &[&[u8]]) -> Result<(Vec<Vec<u8>>, Vec<u8>), B200Error> {
+        let n = kinds.len();
+        self.prove(true, kinds, fields, unsafe { afx_request_num_fields(n as u16) }, n + 9)
+    }
+
+    /// Batch `AnonymousCredential::show`: fields per `afx_show`; returns the presentation's words.
+    pub fn show(&self, kinds: &[u8], fields: &[&[u8]]) -> Result<(Vec<Vec<u8>>, Vec<u8>), B200Error> {
+        let n_in = unsafe { afx_show_num_fields(kinds.len() as u16, kinds.as_ptr()) };
+        let n_out = unsafe { afx_presentation_num_fields(kinds.len() as u16, kinds.as_ptr()) };
+        self.prove(false, kinds, fields, n_in, n_out)
+    }
+}
+
+impl Drop for B200Context {
+    /// Zeroizes the device and host copies of the secret key (src/amacs.rs:64-82 semantics) and frees the context.
+    fn drop(&mut self) {
+        unsafe { afx_ctx_destroy(self.ctx) }
+    }
+}
+
+#[allow(dead_code)]
+fn _assert_c_void_is_unused(_: *const c_void) {}
