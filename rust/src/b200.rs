@@ -4,7 +4,7 @@
 //! reference's own byte encodings: `SystemParameters::to_bytes()` (src/parameters.rs:155-184), the 64 bytes `C_W || I`
 //! (src/issuer.rs:155,163), `amacs::SecretKey::to_bytes()` (src/amacs.rs:110-125), canonical scalars and compressed points.
 
-use std::os::raw::{c_char, c_int, c_void};
+use std::os::raw::{c_char, c_int};
 
 #[repr(C)]
 pub struct afx_ctx {
@@ -169,6 +169,3 @@ impl Drop for B200Context {
         unsafe { afx_ctx_destroy(self.ctx) }
     }
 }
-
-#[allow(dead_code)]
-fn _assert_c_void_is_unused(_: *const c_void) {}
