@@ -126,6 +126,84 @@ __global__ void __launch_bounds__(TPB) k_transcript(Workspace ws, const TxDesc* 
     if (item < ws.count) transcript_job(ws, txs[blockIdx.y], item);
 }
 
+__global__ void __launch_bounds__(256) k_commit_compare(Workspace ws, const CmpPair* pairs) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.count) commit_compare_job(ws, pairs[blockIdx.y], item);
+}
+
+// ---- random-linear-combination path (BatchableProof): coefficients, Pippenger bucket method, final check -------------------
+__global__ void __launch_bounds__(128) k_rlc_scalars(Workspace ws, const RlcDesc* d, RlcBuffers rb) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.count) rlc_scalars_job(ws, *d, rb, item);
+}
+// one CTA per constant term: chunk-wide sum of its coefficients mod l (9-word partial sums, shared-memory tree)
+__global__ void __launch_bounds__(256) k_rlc_colsum(Workspace ws, RlcBuffers rb) {
+    __shared__ u32 part[256][9];
+    const u32 t = blockIdx.x;
+    u32 acc[9];
+    for (int i = 0; i < 9; i++) acc[i] = 0;
+    for (u32 item = threadIdx.x; item < ws.count; item += blockDim.x) {
+        u32 v[8]; load8(v, rb.cterm + ((size_t)t * ws.count + item) * 8);
+        rlc_add288(acc, v);
+    }
+    for (int i = 0; i < 9; i++) part[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) rlc_add288x(part[threadIdx.x], part[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { sc r = rlc_reduce288(part[0]); for (int i = 0; i < 8; i++) rb.csum[8 * t + i] = r.v[i]; }
+}
+__global__ void __launch_bounds__(256) k_rlc_digits(RlcBuffers rb) {
+    u32 n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < rb.N) rlc_digits_job(rb, n);
+}
+__global__ void k_rlc_scan(RlcBuffers rb) {   // one thread per window: 2^(c-1) <= 32,768 counters each
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < rb.nwin) rlc_scan_job(rb, w);
+}
+__global__ void __launch_bounds__(256) k_rlc_scatter(RlcBuffers rb) {
+    u32 n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < rb.N) rlc_scatter_job(rb, n);
+}
+__global__ void __launch_bounds__(128, 4) k_rlc_buckets(Workspace ws, const RlcDesc* d, RlcBuffers rb) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < rb.nwin * rb.nb) rlc_bucket_job(ws, *d, rb, t / rb.nb, t % rb.nb + 1);
+}
+// sum_b b * B_b of one window per CTA: each thread reduces a segment of buckets by running sums, then the partial sums are
+// combined with warp shuffles (a point is 32 words: 32 shuffles per level) and one shared-memory hop between the warps.
+__device__ __forceinline__ ge ge_shfl_down(const ge& p, u32 delta) {
+    ge r;
+    for (int i = 0; i < 8; i++) {
+        r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], delta); r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], delta);
+        r.Z.v[i] = __shfl_down_sync(0xffffffffu, p.Z.v[i], delta); r.T.v[i] = __shfl_down_sync(0xffffffffu, p.T.v[i], delta);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(256) k_rlc_window_reduce(RlcBuffers rb) {
+    __shared__ u32 warp_sum[8][32];
+    const u32 w = blockIdx.x, T = blockDim.x;
+    const u32 L = (rb.nb + T - 1) / T;
+    u32 lo = threadIdx.x * L + 1, hi = lo + L - 1;
+    if (hi > rb.nb) hi = rb.nb;
+    ge acc = lo <= rb.nb ? rlc_segment_job(rb, w, lo, hi) : ge_identity();
+    for (u32 delta = 16; delta > 0; delta >>= 1) {
+        ge other = ge_shfl_down(acc, delta);
+        acc = ge_add(acc, other);              // lanes beyond the live half add garbage that is never read
+    }
+    if ((threadIdx.x & 31u) == 0) store_ge(warp_sum[threadIdx.x >> 5], acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ge tot = load_ge(warp_sum[0]);
+        for (u32 k = 1; k < T / 32; k++) tot = ge_add(tot, load_ge(warp_sum[k]));
+        store_ge(rb.wsum + (size_t)w * 32, tot);
+    }
+}
+__global__ void k_rlc_final(Workspace ws, const RlcDesc* d, RlcBuffers rb) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) rlc_final_job(ws, *d, rb);
+}
+
+
 __global__ void __launch_bounds__(256) k_verdict(Workspace ws, uint8_t* verdicts) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < ws.count) verdicts[item] = ws.status[item] != 0;
@@ -259,6 +337,22 @@ static void be_launch_out_words(const Workspace& ws, const OutWord* d, u32 nword
 }
 static void be_launch_transcript(const Workspace& ws, const TxDesc* d_txs, u32 ntx, be_stream s) {
     k_transcript<<<grid_for(ws.count, TPB, ntx), TPB, 0, s>>>(ws, d_txs);
+}
+static void be_launch_commit_compare(const Workspace& ws, const CmpPair* d_pairs, u32 npairs, be_stream s) {
+    k_commit_compare<<<grid_for(ws.count, 256, npairs), 256, 0, s>>>(ws, d_pairs);
+}
+// The whole RLC pass of one chunk: coefficients, column sums, Pippenger, final check.  8 launches.
+static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d_desc, u32 ncterms, const RlcBuffers& rb, be_stream s) {
+    cudaMemsetAsync(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4, s);
+    k_rlc_scalars<<<grid_for(ws.count, 128, 1), 128, 0, s>>>(ws, d_desc, rb);
+    if (ncterms) k_rlc_colsum<<<ncterms, 256, 0, s>>>(ws, rb);
+    k_rlc_digits<<<(rb.N + 255) / 256, 256, 0, s>>>(rb);
+    k_rlc_scan<<<(rb.nwin + 31) / 32, 32, 0, s>>>(rb);
+    k_rlc_scatter<<<(rb.N + 255) / 256, 256, 0, s>>>(rb);
+    k_rlc_buckets<<<(rb.nwin * rb.nb + 127) / 128, 128, 0, s>>>(ws, d_desc, rb);
+    k_rlc_window_reduce<<<rb.nwin, 256, 0, s>>>(rb);
+    k_rlc_final<<<1, 32, 0, s>>>(ws, d_desc, rb);
+    return 8;
 }
 static void be_launch_verdict(const Workspace& ws, uint8_t* verdicts, be_stream s) {
     k_verdict<<<grid_for(ws.count, 256, 1), 256, 0, s>>>(ws, verdicts);

@@ -31,10 +31,12 @@ constexpr int CTAB_ENTRIES = 128;  // radix-256 signed digits: multiples 1..128 
 enum : u32 { SC_FIELD = 0, SC_MUL = 1, SC_MULADD = 2 };  // R[f0] | R[f0]*R[f1] | R[f0] + R[f1]*R[f2]
 // A scalar reference R[f] names an input field (f < 0x4000), an issuer-secret row (SREF_SECRET | row: x_0, x_1, y_i, w, w')
 // or a per-item derived scalar (SREF_DERIVED | slot: the wide-reduced t and blindings of Issuer::issue).
-enum : u32 { SREF_SECRET = 0x4000, SREF_DERIVED = 0x8000, SREF_MASK = 0x3fff };
+// SREF_CHAL | proof: the challenge recomputed by transcript `proof` of this item (BatchableProof verification, where the wire
+// carries the commitments and the challenge is derived, not given).
+enum : u32 { SREF_SECRET = 0x4000, SREF_DERIVED = 0x8000, SREF_CHAL = 0xc000, SREF_MASK = 0x3fff };
 struct ScalarSrc { u16 op, f0, f1, f2; };
 
-struct VarTerm { u16 table_slot; u16 neg; ScalarSrc s; };
+struct VarTerm { u16 table_slot; u16 neg; ScalarSrc s; u16 ext_slot, pad; };   // ext_slot: the base in extended coordinates (batchable mode only)
 struct ConstTerm { u16 ctab; u16 neg; ScalarSrc s; };
 // flags.  MSM_ADD_W: add the issuer's W after the ladder (Amac::compute_V, amacs.rs:267).  MSM_COMB: a job with constant
 // bases only is evaluated on the per-issuer radix-16 comb tables ((e * 16^i) * G for every window i): 64 mixed adds per
@@ -60,7 +62,7 @@ struct PointJob {
 struct AmacVar { u16 atab_slot, digit_row; };
 struct AmacPs { u16 ctab, y_row, field_m, pad; };  // (y_i * m_i) * G_m[i] for a revealed scalar attribute
 struct AmacDesc {
-    u16 ext_cv, nvar, nps, out_table_slot, out_comp_slot, pad;
+    u16 ext_cv, nvar, nps, out_table_slot, out_comp_slot, out_ext_slot;   // out_ext_slot: 0xffff = Z is not kept in extended form
     AmacVar var[MAX_ATTRS + 2];
     AmacPs ps[MAX_ATTRS];
 };
@@ -206,6 +208,7 @@ AFX_HD void status_or(const Workspace& ws, u32 item, u32 bits) {
 }
 
 AFX_HD const u32* scalar_ref_ptr(const Workspace& ws, u32 ref, u32 item) {
+    if ((ref & SREF_CHAL) == SREF_CHAL) return ws.chal + ((size_t)(ref & SREF_MASK) * ws.count + item) * 8;
     if (ref & SREF_DERIVED) return ws.derived + ((size_t)(ref & SREF_MASK) * ws.count + item) * 8;
     if (ref & SREF_SECRET) return ws.secsc + 8 * (ref & SREF_MASK);
     return field_ptr(ws, ref, item);
@@ -366,6 +369,7 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
     if (active) {
         store8(comp_ptr(ws, d.out_comp_slot, item), w);
         store_table8(table_ptr(ws, d.out_table_slot, item), z);
+        if (d.out_ext_slot != 0xffff) store_ge(ext_ptr(ws, d.out_ext_slot, item), z);
     }
 }
 
@@ -543,6 +547,197 @@ AFX_HD void out_word_job(const Workspace& ws, const OutWord& d, u32 word, u32 it
         for (int i = 0; i < 8; i++) w[i] = r.v[i];
     }
     store8(out + ((size_t)word * ws.count + item) * 8, w);
+}
+
+// ---- stage: commitment comparison (BatchableProof, exact path) -------------------------------------------------------
+// The recomputed sum resp_k*P_k - c*LHS must equal the commitment on the wire (zkp verify_batchable).
+struct CmpPair { u16 commit_slot, field; };
+AFX_HD void commit_compare_job(const Workspace& ws, const CmpPair& p, u32 item) {
+    u32 a[8], b[8];
+    load8(a, commit_ptr(ws, p.commit_slot, item)); load8(b, field_ptr(ws, p.field, item));
+    u32 x = 0;
+    for (int i = 0; i < 8; i++) x |= a[i] ^ b[i];
+    if (x) status_or(ws, item, ST_CHALLENGE);
+}
+
+// ---- random-linear-combination verification of BatchableProofs -------------------------------------------
+// Every constraint j of every item i of a chunk must satisfy  E_ij = sum_k s_k*P_k - c*LHS - R = 0.  One check replaces all of
+// them:  sum_ij rho_ij * E_ij == 0  with independent 128-bit rho_ij derived from a caller-supplied seed.  The sum is one big
+// multiscalar multiplication: per-item points (ladder bases, LHS points, wire commitments) go through a Pippenger bucket
+// method across the whole chunk; the per-issuer generators only need the chunk-wide sums of their coefficients.
+constexpr int RLC_MAX_INPUTS = 6 * MAX_ATTRS + 16, RLC_MAX_CTERMS = 4 * MAX_ATTRS + 16, RLC_MAX_CONS = 6 * MAX_ATTRS + 8;
+struct RlcDesc {
+    u16 ncons, ninputs, ncterms, pad;
+    u16 first_input[RLC_MAX_CONS + 1];   // inputs of constraint j: [first_input[j], first_input[j+1]); the last one is the wire commitment
+    u16 first_cterm[RLC_MAX_CONS + 1];
+    u16 in_ext[RLC_MAX_INPUTS];          // extended-coordinates slot of input k
+    u16 in_neg[RLC_MAX_INPUTS];
+    ScalarSrc in_s[RLC_MAX_INPUTS];      // its scalar (op 0xffff = the constant 1, used for the commitment with in_neg = 1)
+    u16 ct_ctab[RLC_MAX_CTERMS];         // generator of constant term t
+    u16 ct_neg[RLC_MAX_CTERMS];
+    ScalarSrc ct_s[RLC_MAX_CTERMS];
+};
+struct RlcBuffers {
+    u32* scal;      // [ninputs][count][8]   coefficient of every per-item point
+    u32* cterm;     // [ncterms][count][8]   coefficient contributions of the generators
+    u32* csum;      // [ncterms][8]          their chunk-wide sums mod l
+    u32* keys;      // [nwin][N]             (bucket << 1) | sign of input n in window w
+    u32* sorted;    // [nwin][N]             inputs ordered by bucket: (n << 1) | sign
+    u32* hist;      // [nwin][nb + 1]        bucket sizes -> exclusive offsets
+    u32* cursor;    // [nwin][nb + 1]
+    u32* buckets;   // [nwin][nb][32]        bucket sums (extended coordinates)
+    u32* wsum;      // [nwin][32]            per-window sums
+    u32* result;    // [9]                   compress(total) and the verdict word
+    u32 N, nwin, c, nb;    // inputs in the chunk, windows, window bits, buckets per window = 2^(c-1)
+    u64 seed[4];
+};
+
+// rho_ij: 128 bits out of Keccak-f[1600](seed || item || block), twelve per permutation
+AFX_HD void rlc_rho_block(const RlcBuffers& rb, u32 item, u32 block, u64* st) {
+    for (int i = 0; i < 25; i++) st[i] = 0;
+    for (int i = 0; i < 4; i++) st[i] = rb.seed[i];
+    st[4] = item; st[5] = block; st[6] = 0x434c522d58464175ull;   // "uAFX-RLC"
+    keccak_f1600(st);
+}
+AFX_HD sc rlc_rho(const u64* st, u32 j) {
+    sc r = sc_zero();
+    u64 lo = st[2 * (j % 12)], hi = st[2 * (j % 12) + 1];
+    r.v[0] = (u32)lo; r.v[1] = (u32)(lo >> 32); r.v[2] = (u32)hi; r.v[3] = (u32)(hi >> 32);
+    return r;
+}
+// one thread per item: the coefficient of every input and constant term
+AFX_HD void rlc_scalars_job(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb, u32 item) {
+    u64 st[25];
+    for (u32 j = 0; j < d.ncons; j++) {
+        if (j % 12 == 0) rlc_rho_block(rb, item, j / 12, st);
+        sc rho = rlc_rho(st, j);
+        for (u32 k = d.first_input[j]; k < d.first_input[j + 1]; k++) {
+            sc v = d.in_s[k].op == 0xffff ? rho : sc_mul(rho, eval_scalar(ws, d.in_s[k], item));
+            if (d.in_neg[k]) v = sc_neg(v);
+            store8(rb.scal + ((size_t)k * ws.count + item) * 8, v.v);
+        }
+        for (u32 t = d.first_cterm[j]; t < d.first_cterm[j + 1]; t++) {
+            sc v = sc_mul(rho, eval_scalar(ws, d.ct_s[t], item));
+            if (d.ct_neg[t]) v = sc_neg(v);
+            store8(rb.cterm + ((size_t)t * ws.count + item) * 8, v.v);
+        }
+    }
+}
+// sum of a column of canonical scalars mod l (sequential form; the device kernel strides and tree-reduces 9-word partials)
+AFX_HD void rlc_add288(u32* acc /*9 words*/, const u32* v /*8 words*/) {
+    u64 c = 0;
+    for (int i = 0; i < 8; i++) { c += (u64)acc[i] + v[i]; acc[i] = (u32)c; c >>= 32; }
+    acc[8] += (u32)c;
+}
+AFX_HD void rlc_add288x(u32* acc, const u32* v /*9 words*/) {
+    u64 c = 0;
+    for (int i = 0; i < 9; i++) { c += (u64)acc[i] + v[i]; acc[i] = (u32)c; c >>= 32; }
+}
+AFX_HD sc rlc_reduce288(const u32* acc) {
+    u32 x[16];
+    for (int i = 0; i < 16; i++) x[i] = i < 9 ? acc[i] : 0;
+    return sc_reduce512(x);
+}
+// signed base-2^c digits of a canonical scalar: digit w in [-2^(c-1), 2^(c-1)]
+AFX_HD void rlc_digits_job(const RlcBuffers& rb, u32 n) {
+    u32 v[9]; load8(v, rb.scal + (size_t)n * 8); v[8] = 0;
+    u32 carry = 0;
+    const u32 half = 1u << (rb.c - 1), mask = (1u << rb.c) - 1u;
+    for (u32 w = 0; w < rb.nwin; w++) {
+        u32 bit = w * rb.c, word = bit >> 5, sh = bit & 31;
+        u64 two = word < 8 ? ((u64)v[word] | ((u64)v[word + 1] << 32)) : 0;
+        u32 dgt = (u32)((two >> sh) & mask) + carry;
+        u32 neg = dgt > half;
+        carry = neg;
+        u32 mag = neg ? (1u << rb.c) - dgt : dgt;
+        rb.keys[(size_t)w * rb.N + n] = (mag << 1) | neg;
+        if (mag) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(rb.hist + (size_t)w * (rb.nb + 1) + mag, 1u);
+#else
+            rb.hist[(size_t)w * (rb.nb + 1) + mag]++;
+#endif
+        }
+    }
+}
+// hist[w][b] -> exclusive offsets (in place), cursor = copy; hist[w][0] is unused (digit 0 adds nothing)
+AFX_HD void rlc_scan_job(const RlcBuffers& rb, u32 w) {
+    u32* h = rb.hist + (size_t)w * (rb.nb + 1);
+    u32* cur = rb.cursor + (size_t)w * (rb.nb + 1);
+    u32 run = 0;
+    for (u32 b = 1; b <= rb.nb; b++) { u32 cnt = h[b]; h[b] = run; cur[b] = run; run += cnt; }
+    h[0] = run;   // total number of non-zero digits of the window
+}
+AFX_HD void rlc_scatter_job(const RlcBuffers& rb, u32 n) {
+    for (u32 w = 0; w < rb.nwin; w++) {
+        u32 key = rb.keys[(size_t)w * rb.N + n], mag = key >> 1;
+        if (!mag) continue;
+        u32* cur = rb.cursor + (size_t)w * (rb.nb + 1) + mag;
+#if defined(__CUDA_ARCH__)
+        u32 pos = atomicAdd(cur, 1u);
+#else
+        u32 pos = (*cur)++;
+#endif
+        rb.sorted[(size_t)w * rb.N + pos] = (n << 1) | (key & 1u);
+    }
+}
+// one thread per (window, bucket): the sum of the bucket's points
+AFX_HD void rlc_bucket_job(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb, u32 w, u32 b /*1..nb*/) {
+    const u32* h = rb.hist + (size_t)w * (rb.nb + 1);
+    u32 lo = h[b], hi = b < rb.nb ? h[b + 1] : h[0];
+    ge acc = ge_identity();
+    for (u32 q = lo; q < hi; q++) {
+        u32 e = rb.sorted[(size_t)w * rb.N + q], n = e >> 1;
+        u32 k = n / ws.count, item = n - k * ws.count;
+        ge p = load_ge(ext_ptr(ws, d.in_ext[k], item));
+        if (e & 1u) p = ge_neg(p);
+        acc = ge_add(acc, p);
+    }
+    store_ge(rb.buckets + ((size_t)w * rb.nb + (b - 1)) * 32, acc);
+}
+AFX_HD ge ge_mul_small(const ge& p, u32 m) {     // m < 2^16, public
+    ge acc = ge_identity();
+    pniels pn = ge_to_pniels(p);
+    for (int bit = 15; bit >= 0; bit--) {
+        acc = ge_dbl(acc, true);
+        if ((m >> bit) & 1u) acc = ge_add_pn(acc, pn, true);
+    }
+    return acc;
+}
+// contribution of buckets [lo, hi] (1-based) of window w to sum_b b*B_b: running sums, then (lo-1) * (segment sum)
+AFX_HD ge rlc_segment_job(const RlcBuffers& rb, u32 w, u32 lo, u32 hi) {
+    ge run = ge_identity(), tot = ge_identity();
+    for (u32 b = hi; b >= lo; b--) {
+        run = ge_add(run, load_ge(rb.buckets + ((size_t)w * rb.nb + (b - 1)) * 32));
+        tot = ge_add(tot, run);
+        if (b == lo) break;
+    }
+    if (lo > 1) tot = ge_add(tot, ge_mul_small(run, lo - 1));
+    return tot;
+}
+// total = sum_w 2^(c*w) * S_w + sum_t csum[t] * G_t ; result = its encoding (all-zero iff the combination vanishes)
+AFX_HD void rlc_final_job(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb) {
+    ge acc = ge_identity();
+    for (int w = (int)rb.nwin - 1; w >= 0; w--) {
+        for (u32 k = 0; k < rb.c; k++) acc = ge_dbl(acc, true);
+        acc = ge_add(acc, load_ge(rb.wsum + (size_t)w * 32));
+    }
+    for (u32 t = 0; t < d.ncterms; t++) {
+        u32 rec[8];
+        sc_recode16(rec, sc_from_words(rb.csum + 8 * t));
+        const u32* comb = ws.comb + (size_t)d.ct_ctab[t] * COMB_WINDOWS * COMB_ENTRIES * 24;
+        for (int i = 0; i < COMB_WINDOWS; i++) {
+            int dig = sc_digit16(rec, i);
+            if (dig != 0) {
+                u32 mag = (u32)(dig < 0 ? -dig : dig);
+                acc = ge_madd(acc, aniels_cneg(load_aniels(comb + ((size_t)i * COMB_ENTRIES + (mag - 1)) * 24), (u32)dig >> 31), true);
+            }
+        }
+    }
+    u32 wv[8], x = 0;
+    ge_compress(wv, acc);
+    for (int i = 0; i < 8; i++) { rb.result[i] = wv[i]; x |= wv[i]; }
+    rb.result[8] = x == 0;
 }
 
 // ---- stage: transcript -------------------------------------------------------------------------------------------

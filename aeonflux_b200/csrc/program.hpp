@@ -112,6 +112,11 @@ struct TxBuilder {
         append_message("ptvar", label, std::strlen(label));
         append_header("val", 32); begin_op(2, false); absorb_hole(kind, idx);
     }
+    void blinding_commitment_wire(const char* label, u32 field) {   // verify_batchable: validate_and_append_blinding_commitment
+        TxIdCheck c; c.src_kind = (u16)SRC_FIELD; c.src_idx = (u16)field; ids.push_back(c);
+        append_message("blindcom", label, std::strlen(label));
+        append_header("val", 32); begin_op(2, false); absorb_hole(SRC_FIELD, field);
+    }
     void blinding_commitment(const char* label, u32 commit_slot) {
         append_message("blindcom", label, std::strlen(label));
         append_header("val", 32); begin_op(2, false); absorb_hole(SRC_COMMIT, commit_slot);
@@ -128,6 +133,10 @@ struct TxBuilder {
 // ---- compiled program --------------------------------------------------------------------------------
 struct ShapeProgram {
     u32 n_fields = 0, n_tables = 0, n_atabs = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
+    bool batchable = false;            // BatchableProof form: commitments on the wire, challenges derived (transcripts run before the MSMs)
+    std::vector<CmpPair> cmp_pairs;    // (recomputed commitment slot, wire commitment field)
+    std::vector<u16> commit_ext;       // extended-coordinates slot of each wire commitment, same order as cmp_pairs' fields
+    std::vector<RlcDesc> rlc;          // one descriptor (batchable mode): inputs / constant terms of the random linear combination
     bool is_issue = false;             // Issuer::issue: constant-schedule MSMs, derived scalars, output words instead of verdicts
     std::vector<DeriveOp> derived;     // per-item derived scalars, slot k = op k
     std::vector<OutWord> out_words;    // prover output words
@@ -155,9 +164,11 @@ struct MsmBuilder {
     MsmDesc d{};
     explicit MsmBuilder(u32 out_slot) { std::memset(&d, 0, sizeof d); d.out_slot = (u16)out_slot; }
     void add_ext(u32 ext_slot) { d.flags |= MSM_ADD_EXT; d.add_ext = (u16)ext_slot; }
+    const std::vector<int>* tab2ext = nullptr;   // batchable mode: extended-coordinates slot of each table's base
     void var(u32 table_slot, ScalarSrc s, bool neg = false) {
         if (d.nvar >= MAX_VAR_TERMS) throw std::length_error("too many variable-base terms");
         VarTerm& t = d.var[d.nvar++]; t.table_slot = (u16)table_slot; t.neg = neg; t.s = s;
+        t.ext_slot = (u16)((tab2ext && table_slot < tab2ext->size()) ? (*tab2ext)[table_slot] : 0xffff); t.pad = 0;
     }
     void con(u32 ctab, ScalarSrc s, bool neg = false) {
         if (d.ncon >= MAX_CONST_TERMS) throw std::length_error("too many constant-base terms");
@@ -200,32 +211,49 @@ inline size_t presentation_num_fields(u32 n, const uint8_t* kinds) {
     return 1 + 3 + hs + 3 + n + r + 14 * hp;
 }
 
-// ProofOfValidCredential::verify as a program (presentation.rs:324-443).
-inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+inline size_t presentation_num_main_constraints(u32 n, const uint8_t* kinds) {
+    size_t nsp = 0, cons = 2;
+    for (u32 i = 0; i < n; i++) nsp += kinds[i] != 3;
+    for (size_t i = 0; i < nsp; i++) cons += kinds[i] != 3;
+    return cons;
+}
+inline size_t batchable_num_fields(u32 n, const uint8_t* kinds) {
+    size_t hp = 0; for (u32 i = 0; i < n; i++) hp += kinds[i] == 3;
+    return presentation_num_fields(n, kinds) - 1 + presentation_num_main_constraints(n, kinds) + 4 * hp;
+}
+
+// ProofOfValidCredential::verify as a program (presentation.rs:324-443).  batchable = the same statement verified from a
+// BatchableProof (zkp verify_batchable): each challenge word of the layout is replaced by that proof's blinding commitments.
+inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const uint8_t* kinds, bool batchable = false) {
     if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
     for (u32 i = 0; i < n; i++) if (kinds[i] > 3) throw std::invalid_argument("bad attribute kind");
     ShapeProgram P;
     // ---- field map
     u32 hs = 0; std::vector<int> ss_rank(n, -1);
     for (u32 i = 0; i < n; i++) if (kinds[i] == 1) ss_rank[i] = (int)hs++;
+    P.batchable = batchable;
+    const u32 nc_main = (u32)presentation_num_main_constraints(n, kinds), ENC_SH = batchable ? 4 : 0;
     u32 f = 0;
-    const u32 F_CHAL = f++; const u32 F_RESP = f; f += 3 + hs;
+    const u32 F_CHAL = f; f += batchable ? nc_main : 1;      // the challenge, or the main proof's commitments
+    const u32 F_RESP = f; f += 3 + hs;
     const u32 F_CX0 = f++, F_CX1 = f++, F_CV = f++; const u32 F_CY = f; f += n;
     std::vector<int> F_REV(n, -1);
     for (u32 i = 0; i < n; i++) if (kinds[i] == 0 || kinds[i] == 2) F_REV[i] = (int)f++;
     std::vector<u32> enc_base, enc_attr;
-    for (u32 i = 0; i < n; i++) if (kinds[i] == 3) { enc_base.push_back(f); enc_attr.push_back(i); f += 14; }
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 3) { enc_base.push_back(f); enc_attr.push_back(i); f += 14 + ENC_SH; }
     P.n_fields = f;
-    P.scalar_fields.push_back((u16)F_CHAL);
+    if (!batchable) P.scalar_fields.push_back((u16)F_CHAL);
     for (u32 k = 0; k < 3 + hs; k++) P.scalar_fields.push_back((u16)(F_RESP + k));
     for (u32 i = 0; i < n; i++) if (kinds[i] == 0) P.scalar_fields.push_back((u16)F_REV[i]);
-    for (u32 b : enc_base) for (u32 k = 0; k < 7; k++) P.scalar_fields.push_back((u16)(b + k));
+    for (u32 b : enc_base) for (u32 k = batchable ? 5 : 0; k < 7 + ENC_SH; k++) P.scalar_fields.push_back((u16)(b + k));
 
     // ---- point jobs
     u32 ntab = 0, natab = 0, next = 0, ncomp = 0;
     enum : u32 { W_TABLE = 1, W_ATAB = 2, W_EXT = 4, W_COMP = 8, W_COMPNEG = 16 };
     struct Slots { int table = -1, atab = -1, ext = -1, comp = -1, compneg = -1; };
+    std::vector<int> tab2ext;
     auto job = [&](int fa, int fb, u32 op, u32 want) {
+        if (batchable && (want & W_TABLE)) want |= W_EXT;            // the RLC path adds the bases themselves, not table entries
         Slots o;
         PointJob j; j.field_a = (int16_t)fa; j.field_b = (int16_t)fb; j.op = (u16)op;
         j.table_slot = (int16_t)(o.table = (want & W_TABLE) ? (int)ntab++ : -1);
@@ -233,6 +261,7 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         j.ext_slot = (int16_t)(o.ext = (want & W_EXT) ? (int)next++ : -1);
         j.comp_slot = (int16_t)(o.comp = (want & W_COMP) ? (int)ncomp++ : -1);
         j.compneg_slot = (int16_t)(o.compneg = (want & W_COMPNEG) ? (int)ncomp++ : -1);
+        if (o.table >= 0) { tab2ext.resize((size_t)o.table + 1, -1); tab2ext[(size_t)o.table] = o.ext; }
         P.point_jobs.push_back(j);
         return o;
     };
@@ -254,6 +283,7 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
     std::vector<EncSlots> es(enc_base.size());
     for (size_t e = 0; e < enc_base.size(); e++) {
         u32 b = enc_base[e];
+        b += ENC_SH;                                                                              // the point words sit 4 further in the batchable layout
         es[e].T_PK = job((int)(b + 7), -1, PJ_COPY, W_TABLE).table;
         { Slots o = job((int)(b + 8), -1, PJ_COPY, W_TABLE | W_COMPNEG); es[e].T_E1 = o.table; es[e].C_NEG_E1 = o.compneg; }  // E1 and compress(-E1) (encryption.rs:184-185)
         es[e].T_CY2 = job((int)(b + 11), -1, PJ_COPY, W_TABLE).table;
@@ -273,21 +303,32 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
     }
     const u32 T_Z = ntab++; const u32 C_Z = ncomp++;
     A.out_table_slot = (u16)T_Z; A.out_comp_slot = (u16)C_Z; P.z_comp_slot = C_Z;
+    A.out_ext_slot = 0xffff;
+    if (batchable) { A.out_ext_slot = (u16)next; tab2ext.resize((size_t)T_Z + 1, -1); tab2ext[T_Z] = (int)next++; }
+    // wire commitments must decode (verify_batchable decompresses them); their extended form feeds the RLC path
+    std::vector<u32> F_COMMITS;     // every commitment field, main proof first, constraint order
+    if (batchable) {
+        for (u32 k = 0; k < nc_main; k++) F_COMMITS.push_back(F_CHAL + k);
+        for (u32 b : enc_base) for (u32 k = 0; k < 5; k++) F_COMMITS.push_back(b + k);
+        for (u32 fc : F_COMMITS) { P.commit_ext.push_back((u16)next); job((int)fc, -1, PJ_COPY, W_EXT); }
+    }
     P.n_tables = ntab; P.n_atabs = natab; P.n_ext = next; P.n_comp = ncomp;
 
     // ---- main proof: constraints (:416-433) and transcript (:355-412)
-    const ScalarSrc R_z = sc_field(F_RESP + 0), R_z0 = sc_field(F_RESP + 1), R_t = sc_field(F_RESP + 2), C_main = sc_field(F_CHAL);
+    const ScalarSrc R_z = sc_field(F_RESP + 0), R_z0 = sc_field(F_RESP + 1), R_t = sc_field(F_RESP + 2),
+                    C_main = batchable ? sc_field(SREF_CHAL | 0) : sc_field(F_CHAL);
+    const std::vector<int>* t2e = batchable ? &tab2ext : nullptr;
     std::vector<u32> nsp;  // original indices of the non-SecretPoint attributes (the compacted C_y list)
     for (u32 i = 0; i < n; i++) if (kinds[i] != 3) nsp.push_back(i);
     u32 slot = 0;
     struct Con { u32 slot; const char* label; };
     std::vector<Con> main_cons;
-    { MsmBuilder m(slot); m.con(ic.id_I(), R_z); m.var(T_Z, C_main, true); P.msms.push_back(m.d); main_cons.push_back({slot++, "Z"}); }
-    { MsmBuilder m(slot); m.var(T_CX0, R_t); m.con(ic.id_Gx0(), R_z0); m.con(ic.id_Gx1(), R_z); m.var(T_CX1, C_main, true);
+    { MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_I(), R_z); m.var(T_Z, C_main, true); P.msms.push_back(m.d); main_cons.push_back({slot++, "Z"}); }
+    { MsmBuilder m(slot); m.tab2ext = t2e; m.var(T_CX0, R_t); m.con(ic.id_Gx0(), R_z0); m.con(ic.id_Gx1(), R_z); m.var(T_CX1, C_main, true);
       P.msms.push_back(m.d); main_cons.push_back({slot++, "C_x_1"}); }
     for (u32 i = 0; i < nsp.size(); i++) {  // compacted-index loop: i indexes kinds / G_y / G_m, nsp[i] is the commitment
         if (kinds[i] == 3) continue;
-        MsmBuilder m(slot); m.con(ic.id_Gy(i), R_z);
+        MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_Gy(i), R_z);
         if (kinds[i] == 1) m.con(ic.id_Gm(i), sc_field(F_RESP + 3 + ss_rank[i]));
         m.var(T_CY[nsp[i]], C_main, true);
         P.msms.push_back(m.d); main_cons.push_back({slot++, "C_y"});
@@ -303,21 +344,28 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("G_y", ic.enc[ic.id_Gy(i)].data());
         for (u32 i = 0; i < n; i++) if (kinds[i] == 1) tb.point_var_const("G_m", ic.enc[ic.id_Gm(i)].data());
         tb.point_var("Z", SRC_COMP, C_Z);
-        for (const Con& c : main_cons) { tb.blinding_commitment(c.label, c.slot); P.dump_commit.push_back(c.slot); }
+        for (size_t k = 0; k < main_cons.size(); k++) {
+            const Con& c = main_cons[k];
+            if (batchable) { tb.blinding_commitment_wire(c.label, F_CHAL + (u32)k); CmpPair cp; cp.commit_slot = (u16)c.slot; cp.field = (u16)(F_CHAL + k); P.cmp_pairs.push_back(cp); }
+            else tb.blinding_commitment(c.label, c.slot);
+            P.dump_commit.push_back(c.slot);
+        }
+        if (batchable && main_cons.size() != nc_main) throw std::logic_error("constraint count");
         tb.challenge();
-        finish_transcript(P, tb, F_CHAL, 0);
+        finish_transcript(P, tb, batchable ? 0xffff : F_CHAL, 0);
     }
     // ---- proofs of encryption (encryption.rs:154-210), one per hidden plaintext attribute (presentation.rs:438-440)
     for (size_t e = 0; e < enc_base.size(); e++) {
-        u32 b = enc_base[e], idx = enc_attr[e];
-        const ScalarSrc c = sc_field(b), r_a = sc_field(b + 1), r_a0 = sc_field(b + 2), r_a1 = sc_field(b + 3), r_m3 = sc_field(b + 4),
-                        r_z = sc_field(b + 5), r_z1 = sc_field(b + 6);
+        const u32 b0 = enc_base[e], idx = enc_attr[e];
+        const u32 b = b0 + ENC_SH;                       // responses at b+1.., points at b+7.. in either layout; commitments at b0..b0+4
+        const ScalarSrc c = batchable ? sc_field(SREF_CHAL | (u32)(1 + e)) : sc_field(b0), r_a = sc_field(b + 1), r_a0 = sc_field(b + 2),
+                        r_a1 = sc_field(b + 3), r_m3 = sc_field(b + 4), r_z = sc_field(b + 5), r_z1 = sc_field(b + 6);
         u32 s_pk, s_d, s_c2p, s_e1, s_c3;
-        { MsmBuilder m(slot); m.con(ic.id_Ga(), r_a); m.con(ic.id_Ga0(), r_a0); m.con(ic.id_Ga1(), r_a1); m.var(es[e].T_PK, c, true); P.msms.push_back(m.d); s_pk = slot++; }
-        { MsmBuilder m(slot); m.con(ic.id_Gy(0), r_z); m.var(es[e].T_E1, r_a, true); m.var(es[e].T_D, c, true); P.msms.push_back(m.d); s_d = slot++; }
-        { MsmBuilder m(slot); m.var(es[e].T_CY2, r_a1); m.var(es[e].T_CY2P, c, true); P.msms.push_back(m.d); s_c2p = slot++; }
-        { MsmBuilder m(slot); m.var(es[e].T_CY2, r_a0); m.var(es[e].T_CY2P, r_m3); m.con(ic.id_Gy(1), r_z1); m.var(es[e].T_E1, c, true); P.msms.push_back(m.d); s_e1 = slot++; }
-        { MsmBuilder m(slot); m.con(ic.id_Gy(2), r_z); m.con(ic.id_Gm(idx), r_m3); m.var(es[e].T_CY3, c, true); P.msms.push_back(m.d); s_c3 = slot++; }
+        { MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_Ga(), r_a); m.con(ic.id_Ga0(), r_a0); m.con(ic.id_Ga1(), r_a1); m.var(es[e].T_PK, c, true); P.msms.push_back(m.d); s_pk = slot++; }
+        { MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_Gy(0), r_z); m.var(es[e].T_E1, r_a, true); m.var(es[e].T_D, c, true); P.msms.push_back(m.d); s_d = slot++; }
+        { MsmBuilder m(slot); m.tab2ext = t2e; m.var(es[e].T_CY2, r_a1); m.var(es[e].T_CY2P, c, true); P.msms.push_back(m.d); s_c2p = slot++; }
+        { MsmBuilder m(slot); m.tab2ext = t2e; m.var(es[e].T_CY2, r_a0); m.var(es[e].T_CY2P, r_m3); m.con(ic.id_Gy(1), r_z1); m.var(es[e].T_E1, c, true); P.msms.push_back(m.d); s_e1 = slot++; }
+        { MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_Gy(2), r_z); m.con(ic.id_Gm(idx), r_m3); m.var(es[e].T_CY3, c, true); P.msms.push_back(m.d); s_c3 = slot++; }
         TxBuilder tb; tb.start("2019/1416 anonymous credentials"); tb.domain_sep("2019/1416 proof of encryption");
         tb.scalar_var("a"); tb.scalar_var("a0"); tb.scalar_var("a1"); tb.scalar_var("m3"); tb.scalar_var("z"); tb.scalar_var("z1");
         tb.point_var("pk", SRC_FIELD, b + 7);
@@ -329,14 +377,37 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         tb.point_var("C_y_1-E2", SRC_COMP, (u32)es[e].C_D);
         tb.point_var("E1", SRC_FIELD, b + 8);
         tb.point_var("-E1", SRC_COMP, (u32)es[e].C_NEG_E1);
-        tb.blinding_commitment("pk", s_pk); tb.blinding_commitment("C_y_1-E2", s_d); tb.blinding_commitment("C_y_2'", s_c2p);
-        tb.blinding_commitment("E1", s_e1); tb.blinding_commitment("C_y_3", s_c3);
-        for (u32 s : {s_pk, s_d, s_c2p, s_e1, s_c3}) P.dump_commit.push_back(s);
+        const char* enc_labels[5] = {"pk", "C_y_1-E2", "C_y_2'", "E1", "C_y_3"};
+        const u32 enc_slots[5] = {s_pk, s_d, s_c2p, s_e1, s_c3};
+        for (u32 k = 0; k < 5; k++) {
+            if (batchable) { tb.blinding_commitment_wire(enc_labels[k], b0 + k); CmpPair cp; cp.commit_slot = (u16)enc_slots[k]; cp.field = (u16)(b0 + k); P.cmp_pairs.push_back(cp); }
+            else tb.blinding_commitment(enc_labels[k], enc_slots[k]);
+            P.dump_commit.push_back(enc_slots[k]);
+        }
         tb.challenge();
-        finish_transcript(P, tb, b, (u32)(1 + e));
+        finish_transcript(P, tb, batchable ? 0xffff : b0, (u32)(1 + e));
     }
     P.n_msm = slot; P.n_proofs = (u32)P.txs.size();
     mark_comb_jobs(P);
+    if (batchable) {   // the same constraints as inputs of one random linear combination per chunk (engine.cuh, RLC section)
+        RlcDesc R; std::memset(&R, 0, sizeof R);
+        u32 ni = 0, nt = 0;
+        if (P.cmp_pairs.size() > RLC_MAX_CONS) throw std::length_error("too many constraints");
+        for (size_t j = 0; j < P.cmp_pairs.size(); j++) {
+            const MsmDesc& m = P.msms[P.cmp_pairs[j].commit_slot];
+            R.first_input[j] = (u16)ni; R.first_cterm[j] = (u16)nt;
+            if (ni + m.nvar + 1 > RLC_MAX_INPUTS || nt + m.ncon > RLC_MAX_CTERMS) throw std::length_error("too many RLC terms");
+            for (u32 k = 0; k < m.nvar; k++) {
+                if (m.var[k].ext_slot == 0xffff) throw std::logic_error("ladder base without extended coordinates");
+                R.in_ext[ni] = m.var[k].ext_slot; R.in_neg[ni] = m.var[k].neg; R.in_s[ni] = m.var[k].s; ni++;
+            }
+            R.in_ext[ni] = P.commit_ext[j]; R.in_neg[ni] = 1; R.in_s[ni].op = 0xffff; ni++;      // - rho * R_wire
+            for (u32 k = 0; k < m.ncon; k++) { R.ct_ctab[nt] = m.con[k].ctab; R.ct_neg[nt] = m.con[k].neg; R.ct_s[nt] = m.con[k].s; nt++; }
+        }
+        R.ncons = (u16)P.cmp_pairs.size(); R.ninputs = (u16)ni; R.ncterms = (u16)nt;
+        R.first_input[R.ncons] = (u16)ni; R.first_cterm[R.ncons] = (u16)nt;
+        P.rlc.push_back(R);
+    }
     return P;
 }
 

@@ -154,6 +154,25 @@ class Issuer:
         """Batch Issuer::verify (issuer.rs:141-147): verdict 0 = Ok(()), 1 = Err(VerificationFailure)."""
         return self._run(self._b.L.afx_verify_presentations, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
 
+    def verify_batchable(self, batch: PresentationBatch, debug=False):
+        """Batch Issuer::verify for presentations whose proofs are BatchableProofs (commitments instead of challenges, see
+        include/aeonflux_b200.h): every constraint of every item is checked exactly."""
+        return self._run(self._b.L.afx_verify_presentations_batchable, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
+
+    def verify_batchable_rlc(self, batch: PresentationBatch, seed: bytes):
+        """BatchableProof presentations checked as one random linear combination per chunk (Pippenger over the whole chunk), with
+        the exact check as fallback for a chunk that does not vanish.  seed: 32 bytes unpredictable to the provers.
+        Returns (verdicts, number of chunks that fell back)."""
+        if len(seed) != 32:
+            raise ValueError("seed must be 32 bytes")
+        ptrs, keep = B._as_fields(batch.fields)
+        cb = B.afx_presentation_batch(len(batch.kinds), batch.kinds, batch.count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        verdicts = np.zeros(batch.count, np.uint8)
+        sd = ctypes.create_string_buffer(bytes(seed), 32)
+        fell_back = ctypes.c_uint32(0)
+        self._b.check(self._b.L.afx_verify_presentations_batchable_rlc(self._h, ctypes.byref(cb), ctypes.addressof(sd), verdicts.ctypes.data, ctypes.byref(fell_back)))
+        return verdicts, int(fell_back.value)
+
     def verify_wire(self, kinds, items, issuance=False):
         """Batch Issuer::verify (or CredentialIssuance::verify) over item-major wire bytes: items = uint8 [count][n_fields][32],
         the concatenation of each item's words.  One H2D copy; no per-field scatter on the host."""

@@ -97,6 +97,25 @@ typedef struct {
 /* Batch CredentialIssuance::verify (src/issuer.rs:48-57 -> src/nizk/issuance.rs:132-218).  Needs no secret key. */
 int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
 
+/* BatchableProof form (opt-in, NOT the reference's encoding).  The reference proves with zkp's CompactProof
+ * (challenge + responses); its authors left zkp's BatchVerifier commented out (src/nizk/presentation.rs:33-34), which needs the
+ * other zkp encoding, BatchableProof = blinding commitments + responses.  These entry points verify presentations whose proofs
+ * travel in that form: the field layout is the presentation layout above with every challenge word replaced by that proof's
+ * commitments in constraint order (main proof: Z, C_x_1, then the C_y constraints; proof of encryption: pk, C_y_1-E2, C_y_2',
+ * E1, C_y_3), i.e. afx_batchable_num_fields() words.  Semantics = zkp 0.7 Verifier::verify_batchable per proof: commitments are
+ * validated (identity / undecodable => reject) and absorbed, the challenge is derived from the transcript, and every constraint
+ * must satisfy sum resp_k*P_k - c*LHS == commitment.  The aMAC recomputation of Z is unchanged (constant schedule).
+ *   afx_verify_presentations_batchable      checks every constraint of every item exactly (one MSM per constraint);
+ *   afx_verify_presentations_batchable_rlc  checks one random linear combination of all constraints of all items of a chunk as
+ *       a single Pippenger multiscalar multiplication (128-bit coefficients derived from `seed`, which must be unpredictable to
+ *       the provers), and falls back to the exact check for a chunk whose combination does not vanish -- so the verdicts are
+ *       the exact ones except with probability ~2^-120 per chunk; fast when rejects are rare. */
+size_t afx_batchable_num_fields(uint16_t n_attrs, const uint8_t* kinds);
+int afx_verify_presentations_batchable(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
+/* exact_chunks (nullable): how many chunks of max_batch items had to fall back to the exact check. */
+int afx_verify_presentations_batchable_rlc(afx_ctx* ctx, const afx_presentation_batch* batch, const uint8_t seed[32], uint8_t* verdicts,
+                                           uint32_t* exact_chunks);
+
 /* Item-major ("wire") variants.  The reference defines no serialization for a presentation or an issuance
  * (src/nizk/presentation.rs:117 "XXX"); the natural one is the concatenation of the item's 32-byte words in
  * the field order documented above, and a batch is the concatenation of its items:

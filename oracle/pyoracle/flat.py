@@ -64,14 +64,43 @@ def _pt(b):
     return p
 
 
-def words_to_presentation(kinds, words) -> Presentation:
+def presentation_num_constraints(kinds) -> int:
+    """Constraints of the main proof: Z, C_x_1 and one per compacted index i whose kinds[i] is not SecretPoint (A.6.1)."""
     kinds = list(kinds)
-    if len(words) != presentation_num_words(kinds):
+    nsp = sum(1 for k in kinds if k != KIND_SP)
+    return 2 + sum(1 for i in range(nsp) if kinds[i] != KIND_SP)
+
+
+def batchable_num_words(kinds) -> int:
+    h_p = sum(1 for k in kinds if k == KIND_SP)
+    return presentation_num_words(kinds) - 1 + presentation_num_constraints(kinds) + 4 * h_p
+
+
+def compact_to_batchable_words(kinds, words, commitments):
+    """The BatchableProof form of a (valid) compact presentation: each challenge word is replaced by that proof's blinding
+    commitments -- which for a valid proof are exactly what verify_compact recomputes (`commitments`, main proof first)."""
+    kinds = list(kinds)
+    nc = presentation_num_constraints(kinds)
+    h_s = sum(1 for k in kinds if k == KIND_SS)
+    r = sum(1 for k in kinds if k in (KIND_PS, KIND_PP))
+    head = 1 + 3 + h_s + 3 + len(kinds) + r
+    out = list(commitments[:nc]) + list(words[1:head])
+    pos, cpos = head, nc
+    for k in kinds:
+        if k == KIND_SP:
+            out += list(commitments[cpos:cpos + 5]) + list(words[pos + 1:pos + ENC_WORDS])
+            pos += ENC_WORDS; cpos += 5
+    return out
+
+
+def words_to_presentation(kinds, words, batchable=False) -> Presentation:
+    kinds = list(kinds)
+    if len(words) != (batchable_num_words(kinds) if batchable else presentation_num_words(kinds)):
         raise ValueError("malformed: word count")
     it = iter(words)
     n = len(kinds)
     hidden = [i for i, k in enumerate(kinds) if k == KIND_SS]
-    c = _sc(next(it))
+    c = [next(it) for _ in range(presentation_num_constraints(kinds))] if batchable else _sc(next(it))
     resp = [_sc(next(it)) for _ in range(3 + len(hidden))]
     C_x_0, C_x_1, C_V = _pt(next(it)), _pt(next(it)), _pt(next(it))
     C_y = [_pt(next(it)) for _ in range(n)]
@@ -87,14 +116,14 @@ def words_to_presentation(kinds, words) -> Presentation:
     for i, k in enumerate(kinds):
         if k != KIND_SP:
             continue
-        ec = _sc(next(it))
+        ec = [next(it) for _ in range(5)] if batchable else _sc(next(it))
         er = [_sc(next(it)) for _ in range(6)]
         pk, E1, E2, C1, C2, C3, C2p = [_pt(next(it)) for _ in range(7)]
         poes.append((i, ProofOfEncryption((ec, er), pk, E1, E2, i, C1, C2, C3, C2p)))
     return Presentation((c, resp), poes, enc_attrs, hidden, C_x_0, C_x_1, C_V, C_y)
 
 
-def verify_flat(issuer, kinds, words):
+def verify_flat(issuer, kinds, words, batchable=False):
     """-> (verdict, trace).  verdict 0 = Ok, 1 = VerificationFailure.
     trace: {'Z': bytes, 'commitments': [bytes...] (main proof's then each enc proof's, in
     constraint order), 'challenges': [32-byte recomputed challenge per proof]} -- filled as far
@@ -103,7 +132,7 @@ def verify_flat(issuer, kinds, words):
     out = {"Z": None, "commitments": [], "challenges": []}
     verdict = 0
     try:
-        p = words_to_presentation(kinds, words)
+        p = words_to_presentation(kinds, words, batchable)
         presentation_verify(p, issuer, trace)
     except VerificationFailure:
         verdict = 1

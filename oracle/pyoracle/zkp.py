@@ -54,7 +54,38 @@ class Verifier:
     def constrain(self, lhs: int, lc):
         self.constraints.append((lhs, list(lc)))
 
-    def verify_compact(self, challenge: int, responses):
+    def verify_batchable(self, commitments, responses):
+        """zkp 0.7 Verifier::verify_batchable (BatchableProof = commitments + responses; the encoding the reference's commented-out
+        BatchVerifier would need, presentation.rs:33-34).  The prover's commitments are validated (identity rejected:
+        validate_and_append_blinding_commitment) and fed to the transcript, the challenge is derived from it, and every
+        constraint must satisfy  sum resp_k * P_k - c * LHS - R == 0.  zkp checks a random 128-bit linear combination of
+        these equations; this restatement checks each one exactly (same verdict up to probability 2^-128)."""
+        if len(responses) != self.num_scalars or len(commitments) != len(self.constraints):
+            raise VerificationFailure("response / commitment count")
+        for (lhs, _lc), enc in zip(self.constraints, commitments):
+            if enc == IDENTITY_COMPRESSED:
+                raise VerificationFailure("identity blinding commitment")
+            self.t.append_message(b"blindcom", self.point_labels[lhs])
+            self.t.append_message(b"val", enc)
+        c = get_challenge(self.t, b"chal")
+        self.trace["challenge"] = c
+        pts = [decompress(e) for e in self.points]
+        Rs = [decompress(e) for e in commitments]
+        if any(p is None for p in pts) or any(r is None for r in Rs):
+            raise VerificationFailure("undecodable point")
+        minus_c = (-c) % L
+        for (lhs, lc), Rw in zip(self.constraints, Rs):
+            acc = Point.identity()
+            for sv, pv in lc:
+                acc = acc + pts[pv] * responses[sv]
+            acc = acc + pts[lhs] * minus_c
+            self.trace["commitments"].append(acc.compress())
+            if not (acc == Rw):
+                raise VerificationFailure("constraint does not hold")
+
+    def verify_compact(self, challenge, responses):
+        if isinstance(challenge, (list, tuple)):       # a BatchableProof travels through the same call sites as (commitments, responses)
+            return self.verify_batchable(list(challenge), responses)
         if len(responses) != self.num_scalars:
             raise VerificationFailure("response count")
         pts = [decompress(e) for e in self.points]

@@ -96,3 +96,16 @@ def golden_issue_request(g, entry):
     rnd = np.frombuffer(rng.fill(64 * (n + 7)), np.uint8).reshape(n + 7, 64).copy()
     attrs = words(entry["issuance_words"][:n])
     return attrs, rnd
+
+
+def to_batchable(kinds, pres, commitments):
+    """Compact presentations [count][W][32] + the commitments their (valid) proofs recompute [count][n_commit][32] -> the
+    BatchableProof layout [count][Wb][32]: every challenge word replaced by that proof's commitments
+    (oracle/pyoracle/flat.py:compact_to_batchable_words gives the word map)."""
+    from oracle.pyoracle import flat as F
+    W, nc = pres.shape[1], commitments.shape[1]
+    order = F.compact_to_batchable_words(list(kinds), [("w", i) for i in range(W)], [("c", j) for j in range(nc)])
+    out = np.empty((pres.shape[0], len(order), 32), np.uint8)
+    for k, (src, idx) in enumerate(order):
+        out[:, k] = pres[:, idx] if src == "w" else commitments[:, idx]
+    return out

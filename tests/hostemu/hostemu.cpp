@@ -64,6 +64,26 @@ static void be_launch_out_words(const Workspace& ws, const OutWord* d, u32 nword
 static void be_launch_transcript(const Workspace& ws, const TxDesc* txs, u32 ntx, be_stream) {
     for (u32 k = 0; k < ntx; k++) for (u32 i = 0; i < ws.count; i++) transcript_job(ws, txs[k], i);
 }
+static void be_launch_commit_compare(const Workspace& ws, const CmpPair* pairs, u32 npairs, be_stream) {
+    for (u32 k = 0; k < npairs; k++) for (u32 i = 0; i < ws.count; i++) commit_compare_job(ws, pairs[k], i);
+}
+static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d, u32 ncterms, const RlcBuffers& rb, be_stream) {
+    std::memset(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4);
+    for (u32 i = 0; i < ws.count; i++) rlc_scalars_job(ws, *d, rb, i);
+    for (u32 t = 0; t < ncterms; t++) {
+        u32 acc[9] = {0};
+        for (u32 i = 0; i < ws.count; i++) rlc_add288(acc, rb.cterm + ((size_t)t * ws.count + i) * 8);
+        sc r = rlc_reduce288(acc);
+        for (int i = 0; i < 8; i++) rb.csum[8 * t + i] = r.v[i];
+    }
+    for (u32 n = 0; n < rb.N; n++) rlc_digits_job(rb, n);
+    for (u32 w = 0; w < rb.nwin; w++) rlc_scan_job(rb, w);
+    for (u32 n = 0; n < rb.N; n++) rlc_scatter_job(rb, n);
+    for (u32 w = 0; w < rb.nwin; w++) for (u32 b = 1; b <= rb.nb; b++) rlc_bucket_job(ws, *d, rb, w, b);
+    for (u32 w = 0; w < rb.nwin; w++) store_ge(rb.wsum + (size_t)w * 32, rlc_segment_job(rb, w, 1, rb.nb));
+    rlc_final_job(ws, *d, rb);
+    return 8;
+}
 static void be_launch_verdict(const Workspace& ws, uint8_t* v, be_stream) { for (u32 i = 0; i < ws.count; i++) v[i] = ws.status[i] != 0; }
 static void be_launch_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encneg, u32* bad, be_stream) {
     for (u32 b = 0; b < ncp; b++) {

@@ -334,3 +334,37 @@ def test_primitives_on_gpu(coracle):
     exp_ok = np.array([L.afxo_decompress_compress(enc[i].ctypes.data, scratch.ctypes.data) for i in range(20000)], np.uint8)
     assert (ok == exp_ok).all() and 1000 < ok.sum() < 1800
     assert (out[ok == 1] == enc[ok == 1]).all()
+
+
+def test_batchable_proofs_exact_and_rlc_on_gpu(readme4):
+    """BatchableProof presentations on the GPU: 20,000 README-4 items over three chunks.  All honest -> every chunk's random
+    linear combination vanishes (no fallback); a few corrupted items -> exactly those are rejected, by the exact path and by
+    the RLC path (which falls back only for the chunks that hold them); different seeds agree."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from tests.common import to_batchable
+    orc, _, (sp, ip, sk) = readme4
+    base = 1000
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"batchable-gpu", 0, base, want_issuances=False)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    assert not ov.any()
+    bp = np.tile(to_batchable(kinds, pres, tr["commitments"]), (20, 1, 1))
+    count = len(bp)
+    iss = Issuer(sp, ip, sk, device=0, max_batch=8192)
+    batch = PresentationBatch.from_items(kinds, bp)
+    assert not iss.verify_batchable(batch).any()
+    v, fell_back = iss.verify_batchable_rlc(batch, bytes(range(32)))
+    assert not v.any() and fell_back == 0
+    rng = np.random.default_rng(51)
+    bad = np.array([5, 8191, 8192, 19999])                      # chunks 0, 0, 1, 2
+    for i in bad:
+        bp[i, rng.integers(0, bp.shape[1]), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+    batch = PresentationBatch.from_items(kinds, bp)
+    expect = np.zeros(count, np.uint8); expect[bad] = 1
+    assert (iss.verify_batchable(batch) == expect).all()
+    for seed in (bytes(range(32)), bytes(32), bytes([7] * 32)):
+        v, fell_back = iss.verify_batchable_rlc(batch, seed)
+        assert (v == expect).all() and fell_back == 3
+    bp[bad[2:]] = np.tile(to_batchable(kinds, pres, tr["commitments"]), (20, 1, 1))[bad[2:]]      # repair chunks 1 and 2
+    v, fell_back = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, bp), bytes(range(32)))
+    expect[bad[2:]] = 0
+    assert (v == expect).all() and fell_back == 1

@@ -303,3 +303,44 @@ def test_primitives_on_emulation(emu, coracle):
     from aeonflux_b200 import Issuer
     sp, ip, sk = coracle.make_issuer(1)
     check_primitives(Issuer(sp, ip, None, max_batch=4, _binding=emu), coracle)
+
+
+@pytest.mark.parametrize("name", ["readme4", "s16", "scalar1", "quirk_sp_middle", "revealed10"])
+def test_batchable_proofs_exact_and_rlc(emu, coracle, name):
+    """BatchableProof presentations (commitments on the wire): the exact per-constraint check and the
+    random-linear-combination / Pippenger check agree with the Python restatement of zkp's verify_batchable -- honest items,
+    a corrupted commitment, a corrupted response, an identity commitment, an undecodable commitment."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from oracle.pyoracle import aeonflux as A, flat as F, ristretto as R
+    from tests.common import to_batchable
+    g = load_golden(name)
+    sp, ip, sk = bytes.fromhex(g["sysparams"]), bytes.fromhex(g["issuer_pub"]), bytes.fromhex(g["secret"])
+    orc = coracle.Issuer(sp, ip, sk)
+    rk = bytes(REQ[k] for k in g["request"])
+    count = 6
+    kinds, pres, _ = orc.synth(rk, g["hide"], g["config"].encode(), 0, count, want_issuances=False)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    assert not ov.any()
+    bp = to_batchable(kinds, pres, tr["commitments"])
+    iss = Issuer(sp, ip, sk, max_batch=4, _binding=emu)
+    assert bp.shape[1] == iss._b.L.afx_batchable_num_fields(len(kinds), kinds)
+    v, dbg = iss.verify_batchable(PresentationBatch.from_items(kinds, bp), debug=True)
+    assert not v.any()
+    assert (dbg["challenges"][0] == pres[:, 0]).all()                # the derived challenge is the compact proof's challenge
+    vr, fell_back = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, bp), bytes(range(32)))
+    assert not vr.any() and fell_back == 0
+    nc = F.presentation_num_constraints(list(kinds))
+    bad = bp.copy()
+    bad[1, 0, 5] ^= 1                                                 # a commitment (still decodes or not: either way rejected)
+    bad[2, nc, 0] ^= 1                                                # a response
+    bad[3, 1] = 0                                                     # an identity commitment
+    bad[4, 0] = 0xff                                                  # an undecodable commitment
+    py = A.Issuer(A.SystemParameters.from_bytes(sp), A.IssuerParameters(R.decompress(ip[:32]), R.decompress(ip[32:])),
+                  A.SecretKey(*[int.from_bytes(sk[4 + 32 * i:36 + 32 * i], "little") for i in range(4)],
+                              [int.from_bytes(sk[132 + 32 * i:164 + 32 * i], "little") for i in range(g["n"])], R.decompress(sk[-32:])))
+    expect = [F.verify_flat(py, kinds, [bad[i, w].tobytes() for w in range(bad.shape[1])], batchable=True)[0] for i in range(count)]
+    assert expect == [0, 1, 1, 1, 1, 0]
+    v = iss.verify_batchable(PresentationBatch.from_items(kinds, bad))
+    assert list(v) == expect
+    vr, fell_back = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, bad), bytes(range(32)))
+    assert list(vr) == expect and fell_back == 2                      # both chunks of 4 and 2 items hold a bad item
