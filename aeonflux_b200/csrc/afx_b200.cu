@@ -154,13 +154,31 @@ __global__ void __launch_bounds__(256) k_rlc_colsum(Workspace ws, RlcBuffers rb)
     }
     if (threadIdx.x == 0) { sc r = rlc_reduce288(part[0]); for (int i = 0; i < 8; i++) rb.csum[8 * t + i] = r.v[i]; }
 }
-__global__ void __launch_bounds__(256) k_rlc_digits(RlcBuffers rb) {
+__global__ void __launch_bounds__(256) k_rlc_digits(const RlcDesc* d, RlcBuffers rb, u32 count) {
     u32 n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < rb.N) rlc_digits_job(rb, n);
+    if (n < rb.N) rlc_digits_job(*d, rb, count, n);
 }
-__global__ void k_rlc_scan(RlcBuffers rb) {   // one thread per window: 2^(c-1) <= 32,768 counters each
-    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < rb.nwin) rlc_scan_job(rb, w);
+// one CTA per window: exclusive scan of the 2^(c-1) bucket sizes (each thread owns a run of consecutive buckets; the run
+// totals are scanned in shared memory), offsets written in place and copied to the scatter cursors
+__global__ void __launch_bounds__(1024) k_rlc_scan(RlcBuffers rb) {
+    __shared__ u32 part[1024];
+    const u32 w = blockIdx.x, T = blockDim.x, L = (rb.nb + T - 1) / T;
+    u32* h = rb.hist + (size_t)w * (rb.nb + 1);
+    u32* cur = rb.cursor + (size_t)w * (rb.nb + 1);
+    const u32 lo = threadIdx.x * L + 1;
+    u32 sum = 0;
+    for (u32 b = lo; b < lo + L && b <= rb.nb; b++) sum += h[b];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (u32 d = 1; d < T; d <<= 1) {                      // Hillis-Steele inclusive scan of the run totals
+        u32 v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = part[threadIdx.x] - sum;
+    for (u32 b = lo; b < lo + L && b <= rb.nb; b++) { u32 cnt = h[b]; h[b] = run; cur[b] = run; run += cnt; }
+    if (threadIdx.x == T - 1) h[0] = part[T - 1];          // total number of non-zero digits of the window
 }
 __global__ void __launch_bounds__(256) k_rlc_scatter(RlcBuffers rb) {
     u32 n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,8 +198,8 @@ __device__ __forceinline__ ge ge_shfl_down(const ge& p, u32 delta) {
     }
     return r;
 }
-__global__ void __launch_bounds__(256) k_rlc_window_reduce(RlcBuffers rb) {
-    __shared__ u32 warp_sum[8][32];
+__global__ void __launch_bounds__(512) k_rlc_window_reduce(RlcBuffers rb) {
+    __shared__ u32 warp_sum[16][32];
     const u32 w = blockIdx.x, T = blockDim.x;
     const u32 L = (rb.nb + T - 1) / T;
     u32 lo = threadIdx.x * L + 1, hi = lo + L - 1;
@@ -199,10 +217,18 @@ __global__ void __launch_bounds__(256) k_rlc_window_reduce(RlcBuffers rb) {
         store_ge(rb.wsum + (size_t)w * 32, tot);
     }
 }
-__global__ void k_rlc_final(Workspace ws, const RlcDesc* d, RlcBuffers rb) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) rlc_final_job(ws, *d, rb);
+// one warp: the lanes share out the generators' fixed-base multiplications (comb tables) while lane 0 also runs the Horner
+// pass over the window sums; a shuffle reduction joins them and lane 0 publishes the verdict of the chunk
+__global__ void __launch_bounds__(32) k_rlc_final(Workspace ws, const RlcDesc* d, RlcBuffers rb) {
+    ge acc = ge_identity();
+    for (u32 t = threadIdx.x; t < d->ncterms; t += 32) acc = ge_add(acc, rlc_cterm_point(ws, *d, rb, t));
+    if (threadIdx.x == 0) acc = ge_add(acc, rlc_horner(rb));
+    for (u32 delta = 16; delta > 0; delta >>= 1) {
+        ge other = ge_shfl_down(acc, delta);
+        acc = ge_add(acc, other);
+    }
+    if (threadIdx.x == 0) rlc_publish(rb, acc);
 }
-
 
 __global__ void __launch_bounds__(256) k_verdict(Workspace ws, uint8_t* verdicts) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,11 +372,11 @@ static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d_desc, u32 ncterms
     cudaMemsetAsync(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4, s);
     k_rlc_scalars<<<grid_for(ws.count, 128, 1), 128, 0, s>>>(ws, d_desc, rb);
     if (ncterms) k_rlc_colsum<<<ncterms, 256, 0, s>>>(ws, rb);
-    k_rlc_digits<<<(rb.N + 255) / 256, 256, 0, s>>>(rb);
-    k_rlc_scan<<<(rb.nwin + 31) / 32, 32, 0, s>>>(rb);
+    k_rlc_digits<<<(rb.N + 255) / 256, 256, 0, s>>>(d_desc, rb, ws.count);
+    k_rlc_scan<<<rb.nwin, 1024, 0, s>>>(rb);
     k_rlc_scatter<<<(rb.N + 255) / 256, 256, 0, s>>>(rb);
     k_rlc_buckets<<<(rb.nwin * rb.nb + 127) / 128, 128, 0, s>>>(ws, d_desc, rb);
-    k_rlc_window_reduce<<<rb.nwin, 256, 0, s>>>(rb);
+    k_rlc_window_reduce<<<rb.nwin, 512, 0, s>>>(rb);
     k_rlc_final<<<1, 32, 0, s>>>(ws, d_desc, rb);
     return 8;
 }

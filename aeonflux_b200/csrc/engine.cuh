@@ -562,7 +562,7 @@ AFX_HD void commit_compare_job(const Workspace& ws, const CmpPair& p, u32 item) 
 
 // ---- random-linear-combination verification of BatchableProofs -------------------------------------------
 // Every constraint j of every item i of a chunk must satisfy  E_ij = sum_k s_k*P_k - c*LHS - R = 0.  One check replaces all of
-// them:  sum_ij rho_ij * E_ij == 0  with independent 128-bit rho_ij derived from a caller-supplied seed.  The sum is one big
+// them:  sum_ij rho_ij * E_ij == 0  with independent 127-bit rho_ij derived from a caller-supplied seed.  The sum is one big
 // multiscalar multiplication: per-item points (ladder bases, LHS points, wire commitments) go through a Pippenger bucket
 // method across the whole chunk; the per-issuer generators only need the chunk-wide sums of their coefficients.
 constexpr int RLC_MAX_INPUTS = 6 * MAX_ATTRS + 16, RLC_MAX_CTERMS = 4 * MAX_ATTRS + 16, RLC_MAX_CONS = 6 * MAX_ATTRS + 8;
@@ -602,7 +602,9 @@ AFX_HD void rlc_rho_block(const RlcBuffers& rb, u32 item, u32 block, u64* st) {
 AFX_HD sc rlc_rho(const u64* st, u32 j) {
     sc r = sc_zero();
     u64 lo = st[2 * (j % 12)], hi = st[2 * (j % 12) + 1];
-    r.v[0] = (u32)lo; r.v[1] = (u32)(lo >> 32); r.v[2] = (u32)hi; r.v[3] = (u32)(hi >> 32);
+    // 127 bits: with bit 127 clear the signed-digit recoding of a bare rho (the commitments' coefficient) never carries out of
+    // its top window -- a carry would put half of all commitments of the chunk into bucket 1 of the next window
+    r.v[0] = (u32)lo; r.v[1] = (u32)(lo >> 32); r.v[2] = (u32)hi; r.v[3] = (u32)(hi >> 32) & 0x7fffffffu;
     return r;
 }
 // one thread per item: the coefficient of every input and constant term
@@ -612,8 +614,9 @@ AFX_HD void rlc_scalars_job(const Workspace& ws, const RlcDesc& d, const RlcBuff
         if (j % 12 == 0) rlc_rho_block(rb, item, j / 12, st);
         sc rho = rlc_rho(st, j);
         for (u32 k = d.first_input[j]; k < d.first_input[j + 1]; k++) {
+            // the sign of an input is applied to its point in the bucket pass, not to the scalar: -rho mod l would share its
+            // upper ~125 bits with every other 128-bit rho and pile all those inputs into the same few buckets
             sc v = d.in_s[k].op == 0xffff ? rho : sc_mul(rho, eval_scalar(ws, d.in_s[k], item));
-            if (d.in_neg[k]) v = sc_neg(v);
             store8(rb.scal + ((size_t)k * ws.count + item) * 8, v.v);
         }
         for (u32 t = d.first_cterm[j]; t < d.first_cterm[j + 1]; t++) {
@@ -639,8 +642,9 @@ AFX_HD sc rlc_reduce288(const u32* acc) {
     return sc_reduce512(x);
 }
 // signed base-2^c digits of a canonical scalar: digit w in [-2^(c-1), 2^(c-1)]
-AFX_HD void rlc_digits_job(const RlcBuffers& rb, u32 n) {
+AFX_HD void rlc_digits_job(const RlcDesc& d, const RlcBuffers& rb, u32 count, u32 n) {
     u32 v[9]; load8(v, rb.scal + (size_t)n * 8); v[8] = 0;
+    const u32 flip = d.in_neg[n / count] & 1u;
     u32 carry = 0;
     const u32 half = 1u << (rb.c - 1), mask = (1u << rb.c) - 1u;
     for (u32 w = 0; w < rb.nwin; w++) {
@@ -650,7 +654,7 @@ AFX_HD void rlc_digits_job(const RlcBuffers& rb, u32 n) {
         u32 neg = dgt > half;
         carry = neg;
         u32 mag = neg ? (1u << rb.c) - dgt : dgt;
-        rb.keys[(size_t)w * rb.N + n] = (mag << 1) | neg;
+        rb.keys[(size_t)w * rb.N + n] = (mag << 1) | (neg ^ flip);
         if (mag) {
 #if defined(__CUDA_ARCH__)
             atomicAdd(rb.hist + (size_t)w * (rb.nb + 1) + mag, 1u);
@@ -716,28 +720,38 @@ AFX_HD ge rlc_segment_job(const RlcBuffers& rb, u32 w, u32 lo, u32 hi) {
     return tot;
 }
 // total = sum_w 2^(c*w) * S_w + sum_t csum[t] * G_t ; result = its encoding (all-zero iff the combination vanishes)
-AFX_HD void rlc_final_job(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb) {
+AFX_HD ge rlc_horner(const RlcBuffers& rb) {
     ge acc = ge_identity();
     for (int w = (int)rb.nwin - 1; w >= 0; w--) {
         for (u32 k = 0; k < rb.c; k++) acc = ge_dbl(acc, true);
         acc = ge_add(acc, load_ge(rb.wsum + (size_t)w * 32));
     }
-    for (u32 t = 0; t < d.ncterms; t++) {
-        u32 rec[8];
-        sc_recode16(rec, sc_from_words(rb.csum + 8 * t));
-        const u32* comb = ws.comb + (size_t)d.ct_ctab[t] * COMB_WINDOWS * COMB_ENTRIES * 24;
-        for (int i = 0; i < COMB_WINDOWS; i++) {
-            int dig = sc_digit16(rec, i);
-            if (dig != 0) {
-                u32 mag = (u32)(dig < 0 ? -dig : dig);
-                acc = ge_madd(acc, aniels_cneg(load_aniels(comb + ((size_t)i * COMB_ENTRIES + (mag - 1)) * 24), (u32)dig >> 31), true);
-            }
+    return acc;
+}
+AFX_HD ge rlc_cterm_point(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb, u32 t) {   // csum[t] * G_t on the comb tables
+    ge acc = ge_identity();
+    u32 rec[8];
+    sc_recode16(rec, sc_from_words(rb.csum + 8 * t));
+    const u32* comb = ws.comb + (size_t)d.ct_ctab[t] * COMB_WINDOWS * COMB_ENTRIES * 24;
+    for (int i = 0; i < COMB_WINDOWS; i++) {
+        int dig = sc_digit16(rec, i);
+        if (dig != 0) {
+            u32 mag = (u32)(dig < 0 ? -dig : dig);
+            acc = ge_madd(acc, aniels_cneg(load_aniels(comb + ((size_t)i * COMB_ENTRIES + (mag - 1)) * 24), (u32)dig >> 31), true);
         }
     }
+    return acc;
+}
+AFX_HD void rlc_publish(const RlcBuffers& rb, const ge& total) {
     u32 wv[8], x = 0;
-    ge_compress(wv, acc);
+    ge_compress(wv, total);
     for (int i = 0; i < 8; i++) { rb.result[i] = wv[i]; x |= wv[i]; }
     rb.result[8] = x == 0;
+}
+AFX_HD void rlc_final_job(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb) {
+    ge acc = rlc_horner(rb);
+    for (u32 t = 0; t < d.ncterms; t++) acc = ge_add(acc, rlc_cterm_point(ws, d, rb, t));
+    rlc_publish(rb, acc);
 }
 
 // ---- stage: transcript -------------------------------------------------------------------------------------------

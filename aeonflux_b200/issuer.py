@@ -48,6 +48,27 @@ class PresentationBatch:
         return PresentationBatch(kinds, np.ascontiguousarray(np.asarray(items, dtype=np.uint8).transpose(1, 0, 2)))
 
 
+def compact_to_batchable(kinds, fields, commitments):
+    """Re-encode compact presentations as BatchableProof presentations: fields [n_fields][count][32] in the compact layout and
+    the blinding commitments their proofs recompute [n_commitments][count][32] (e.g. the `commitments` of verify_batch(debug=True))
+    -> fields in the batchable layout (every challenge word replaced by that proof's commitments, include/aeonflux_b200.h)."""
+    kinds = list(bytes(kinds))
+    n = len(kinds)
+    h_s = sum(k == KIND_SECRET_SCALAR for k in kinds)
+    r = sum(k in (KIND_PUBLIC_SCALAR, KIND_PUBLIC_POINT) for k in kinds)
+    nsp = sum(k != KIND_SECRET_POINT for k in kinds)
+    nc = 2 + sum(kinds[i] != KIND_SECRET_POINT for i in range(nsp))
+    head = 1 + 3 + h_s + 3 + n + r
+    rows = [commitments[j] for j in range(nc)] + [fields[w] for w in range(1, head)]
+    pos, cpos = head, nc
+    for k in kinds:
+        if k == KIND_SECRET_POINT:
+            rows += [commitments[cpos + j] for j in range(5)] + [fields[w] for w in range(pos + 1, pos + 14)]
+            pos += 14
+            cpos += 5
+    return np.ascontiguousarray(np.stack(rows))
+
+
 IssuanceBatch = PresentationBatch   # same container; kinds are 0 (scalar attribute) / 2 (point attribute)
 
 

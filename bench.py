@@ -229,6 +229,21 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     assert int(verdicts_dev.sum().item()) == 0, "presentations made on the device failed Issuer::verify"
     out["show_4attr_revealed"] = {"workload": "batch AnonymousCredential::show of %d all-revealed 4-attribute credentials (user-side prover), verified afterwards" % B,
                                   "value": B / (ms * 1e-3), "unit": "presentations/s", "ms_per_step": ms}
+    # ---- BatchableProof mode (opt-in, not the reference's encoding): the same presentations re-encoded with their commitments,
+    # verified exactly and by one random linear combination per batch (Pippenger); host-buffer calls, wall clock
+    from aeonflux_b200 import PresentationBatch, compact_to_batchable
+    comp = PresentationBatch.from_items(KINDS_README4, items4[:B])
+    _, dbg = issuer4.verify_batch(comp, debug=True)
+    bb = PresentationBatch(KINDS_README4, compact_to_batchable(KINDS_README4, comp.fields, dbg["commitments"]))
+    for name, fn in (("verify_batchable_exact", lambda: issuer4.verify_batchable(bb)), ("verify_batchable_rlc", lambda: issuer4.verify_batchable_rlc(bb, bytes(range(32)))[0])):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            v = fn()
+        dt = (time.perf_counter() - t0) / steps
+        assert not v.any()
+        out[name] = {"workload": "%d README-4 presentations in BatchableProof form through the host-buffer call (%s), all valid" % (B, "one MSM per constraint" if "exact" in name else "one random linear combination per batch, Pippenger"),
+                     "value": B / dt, "unit": "presentations/s", "ms_per_step": dt * 1e3, "timing": "end to end (H2D + kernels + D2H), wall clock"}
     # ---- S16 presentations (configs[3]) at the config's full batch: 65,536 x 4,576 B in, 4.6 GB of ladder tables
     try:
         blob = open(os.path.join(ROOT, "bench_data", "issuer16.bin"), "rb").read()

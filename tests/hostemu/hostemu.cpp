@@ -76,7 +76,7 @@ static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d, u32 ncterms, con
         sc r = rlc_reduce288(acc);
         for (int i = 0; i < 8; i++) rb.csum[8 * t + i] = r.v[i];
     }
-    for (u32 n = 0; n < rb.N; n++) rlc_digits_job(rb, n);
+    for (u32 n = 0; n < rb.N; n++) rlc_digits_job(*d, rb, ws.count, n);
     for (u32 w = 0; w < rb.nwin; w++) rlc_scan_job(rb, w);
     for (u32 n = 0; n < rb.N; n++) rlc_scatter_job(rb, n);
     for (u32 w = 0; w < rb.nwin; w++) for (u32 b = 1; b <= rb.nb; b++) rlc_bucket_job(ws, *d, rb, w, b);
