@@ -134,6 +134,7 @@ struct TxBuilder {
 struct ShapeProgram {
     u32 n_fields = 0, n_tables = 0, n_atabs = 0, n_ext = 0, n_comp = 0, n_msm = 0, n_proofs = 0;
     bool batchable = false;            // BatchableProof form: commitments on the wire, challenges derived (transcripts run before the MSMs)
+    u32 n_point_jobs_amac = 0;         // the first point jobs feed the aMAC ladder (batchable mode runs the rest beside it)
     std::vector<CmpPair> cmp_pairs;    // (recomputed commitment slot, wire commitment field)
     std::vector<u16> commit_ext;       // extended-coordinates slot of each wire commitment, same order as cmp_pairs' fields
     std::vector<RlcDesc> rlc;          // one descriptor (batchable mode): inputs / constant terms of the random linear combination
@@ -279,6 +280,7 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
             T_CY[i] = o.table; A_X[i] = o.atab;
         }
     }
+    P.n_point_jobs_amac = (u32)P.point_jobs.size();
     struct EncSlots { int T_PK, T_E1, C_NEG_E1, T_CY2, T_CY3, T_CY2P, T_D, C_D; };
     std::vector<EncSlots> es(enc_base.size());
     for (size_t e = 0; e < enc_base.size(); e++) {

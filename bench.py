@@ -234,7 +234,8 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     from aeonflux_b200 import PresentationBatch, compact_to_batchable
     comp = PresentationBatch.from_items(KINDS_README4, items4[:B])
     _, dbg = issuer4.verify_batch(comp, debug=True)
-    bb = PresentationBatch(KINDS_README4, compact_to_batchable(KINDS_README4, comp.fields, dbg["commitments"]))
+    bb_host = torch.from_numpy(compact_to_batchable(KINDS_README4, comp.fields, dbg["commitments"])).pin_memory()
+    bb = PresentationBatch(KINDS_README4, bb_host.numpy())
     for name, fn in (("verify_batchable_exact", lambda: issuer4.verify_batchable(bb)), ("verify_batchable_rlc", lambda: issuer4.verify_batchable_rlc(bb, bytes(range(32)))[0])):
         fn()
         t0 = time.perf_counter()

@@ -117,6 +117,18 @@ public:
         if (rc != AFX_OK) throw Error(rc);
         return to_results(v);
     }
+    // Opt-in BatchableProof form (commitments instead of challenges; not the reference's encoding, see aeonflux_b200.h):
+    // exact per-constraint check, or one random linear combination per chunk with the exact check as fallback.
+    std::vector<Result<>> verify_batchable(const PresentationBatch& p, const uint8_t* rlc_seed32 = nullptr) const {
+        if (p.fields.size() != afx_batchable_num_fields((uint16_t)p.kinds.size(), p.kinds.data())) throw std::invalid_argument("wrong number of batchable fields");
+        auto ptrs = p.pointers();
+        afx_presentation_batch b{(uint16_t)p.kinds.size(), p.kinds.data(), p.count(), ptrs.data(), ptrs.size()};
+        std::vector<uint8_t> v(p.count());
+        int rc = rlc_seed32 ? afx_verify_presentations_batchable_rlc(ctx_, &b, rlc_seed32, v.data(), nullptr)
+                            : afx_verify_presentations_batchable(ctx_, &b, v.data(), nullptr);
+        if (rc != AFX_OK) throw Error(rc);
+        return to_results(v);
+    }
     // ... over item-major wire bytes ([count][n_fields][32])
     std::vector<Result<>> verify_wire(const std::vector<uint8_t>& kinds, const uint8_t* items, size_t count) const {
         std::vector<uint8_t> v(count);
