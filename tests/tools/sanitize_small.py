@@ -28,5 +28,16 @@ for n, rk, hide, count in ((4, b"SSPE", [0, 3], 300), (3, b"SES", [1], 70), (16,
     out, status, _ = orc.issue(ik, np.ascontiguousarray(issu[:, :n]), R)
     ires, ist = iss.issue_batch(RequestBatch.from_request(ik, np.ascontiguousarray(issu[:, :n]), R))
     assert (ires.fields.transpose(1, 0, 2)[:, n:] == out).all()
+    # BatchableProof mode: exact and random-linear-combination paths (incl. a fallback chunk)
+    from aeonflux_b200 import compact_to_batchable
+    comp = PresentationBatch.from_items(kinds, pres)
+    _, dbg = iss.verify_batch(comp, debug=True)
+    bf = compact_to_batchable(kinds, comp.fields, dbg["commitments"])
+    assert not iss.verify_batchable(PresentationBatch(kinds, bf)).any()
+    vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes(range(32)))
+    assert not vr.any() and fb == 0
+    bf[1, 3, 2] ^= 1
+    vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes(range(32)))
+    assert vr[3] == 1 and vr.sum() == 1 and fb == 1
     iss.close()
     print("ok", n, rk)
