@@ -126,6 +126,12 @@ __global__ void __launch_bounds__(TPB) k_transcript(Workspace ws, const TxDesc* 
     if (item < ws.count) transcript_job(ws, txs[blockIdx.y], item);
 }
 
+// ladder table of Z from its extended coordinates (exact fallback of an RLC chunk whose front half skipped the tables)
+__global__ void __launch_bounds__(128) k_ztable(Workspace ws, const AmacDesc* d) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.count) ztable_job(ws, *d, item);
+}
+
 __global__ void __launch_bounds__(256) k_commit_compare(Workspace ws, const CmpPair* pairs) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < ws.count) commit_compare_job(ws, pairs[blockIdx.y], item);
@@ -364,6 +370,7 @@ static void be_launch_out_words(const Workspace& ws, const OutWord* d, u32 nword
 static void be_launch_transcript(const Workspace& ws, const TxDesc* d_txs, u32 ntx, be_stream s) {
     k_transcript<<<grid_for(ws.count, TPB, ntx), TPB, 0, s>>>(ws, d_txs);
 }
+static void be_launch_ztable(const Workspace& ws, const AmacDesc* d, be_stream s) { k_ztable<<<grid_for(ws.count, 128, 1), 128, 0, s>>>(ws, d); }
 static void be_launch_commit_compare(const Workspace& ws, const CmpPair* d_pairs, u32 npairs, be_stream s) {
     k_commit_compare<<<grid_for(ws.count, 256, npairs), 256, 0, s>>>(ws, d_pairs);
 }

@@ -98,6 +98,7 @@ struct Workspace {
     const u32* fields;   // struct-of-arrays [n_fields][count][8] (fs_field = count, fs_item = 1) or item-major "wire"
                          // [count][n_fields][8] (fs_field = 1, fs_item = n_fields); strides in 32-byte words
     u32 fs_field, fs_item;
+    u32 no_tables;       // 1: point jobs skip the standard ladder tables (BatchableProof RLC pass: only its exact fallback walks them)
     u32* tables;         // [n_tables][count][8 entries][32]
     u32* atabs;          // [n_atabs][ceil(count/32)][8 entries][8 quads][32 lanes][4]  aMAC tables, warp-transposed
     u32* ext;            // [n_ext][count][32]
@@ -252,8 +253,9 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
     if (j.ext_slot >= 0) store_ge(ext_ptr(ws, (u32)j.ext_slot, item), p);
     if (j.comp_slot >= 0) { ge_compress(w, p); store8(comp_ptr(ws, (u32)j.comp_slot, item), w); }
     if (j.compneg_slot >= 0) { ge_compress(w, ge_neg(p)); store8(comp_ptr(ws, (u32)j.compneg_slot, item), w); }
-    if (j.table_slot >= 0 || j.atab_slot >= 0)
-        store_table8(j.table_slot >= 0 ? table_ptr(ws, (u32)j.table_slot, item) : nullptr, p,
+    const bool want_table = j.table_slot >= 0 && !ws.no_tables;
+    if (want_table || j.atab_slot >= 0)
+        store_table8(want_table ? table_ptr(ws, (u32)j.table_slot, item) : nullptr, p,
                      j.atab_slot >= 0 ? atab_ptr(ws, (u32)j.atab_slot, item) : nullptr);
 }
 
@@ -368,9 +370,13 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
     ge_compress(w, z);
     if (active) {
         store8(comp_ptr(ws, d.out_comp_slot, item), w);
-        store_table8(table_ptr(ws, d.out_table_slot, item), z);
+        if (!ws.no_tables) store_table8(table_ptr(ws, d.out_table_slot, item), z);
         if (d.out_ext_slot != 0xffff) store_ge(ext_ptr(ws, d.out_ext_slot, item), z);
     }
+}
+
+AFX_HD void ztable_job(const Workspace& ws, const AmacDesc& d, u32 item) {
+    store_table8(table_ptr(ws, d.out_table_slot, item), load_ge(ext_ptr(ws, d.out_ext_slot, item)));
 }
 
 // Where constant term k's radix-256 table lives: the first `nstage` are staged in shared memory by the CTA.

@@ -64,6 +64,7 @@ static void be_launch_out_words(const Workspace& ws, const OutWord* d, u32 nword
 static void be_launch_transcript(const Workspace& ws, const TxDesc* txs, u32 ntx, be_stream) {
     for (u32 k = 0; k < ntx; k++) for (u32 i = 0; i < ws.count; i++) transcript_job(ws, txs[k], i);
 }
+static void be_launch_ztable(const Workspace& ws, const AmacDesc* d, be_stream) { for (u32 i = 0; i < ws.count; i++) ztable_job(ws, *d, i); }
 static void be_launch_commit_compare(const Workspace& ws, const CmpPair* pairs, u32 npairs, be_stream) {
     for (u32 k = 0; k < npairs; k++) for (u32 i = 0; i < ws.count; i++) commit_compare_job(ws, pairs[k], i);
 }
