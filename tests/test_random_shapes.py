@@ -26,6 +26,19 @@ def run_shapes(coracle, binding, seed, trials, count, device_kw):
         assert ov[count // 2] == 1
         seen_reject += int(ov[0] == 1); seen_accept += int(ov[0] == 0)
         pres[count // 2, 1, 7] ^= 4
+        if not ov[0]:            # BatchableProof form of the same (honest) presentations: exact and random-linear-combination checks
+            from aeonflux_b200 import compact_to_batchable
+            comp = PresentationBatch.from_items(kinds, pres)
+            _, cdbg = iss.verify_batch(comp, debug=True)
+            bf = compact_to_batchable(kinds, comp.fields, cdbg["commitments"])
+            assert not iss.verify_batchable(PresentationBatch(kinds, bf)).any()
+            vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes([trial] * 32))
+            assert not vr.any() and fb == 0, (n, rk, hide)
+            bf[int(rng.integers(0, bf.shape[0])), count - 1, int(rng.integers(0, 31))] ^= 1 << int(rng.integers(0, 8))
+            expect = np.zeros(count, np.uint8); expect[count - 1] = 1
+            assert (iss.verify_batchable(PresentationBatch(kinds, bf)) == expect).all()
+            vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes([trial] * 32))
+            assert (vr == expect).all() and fb >= 1, (n, rk, hide)
         res, st = iss.show_batch(kinds, np.ascontiguousarray(showin.transpose(1, 0, 2)))
         assert not st.any() and (res.fields.transpose(1, 0, 2) == pres).all(), (n, rk, hide)
         ik = bytes(0 if c == ord("S") else 2 for c in rk)
