@@ -437,6 +437,8 @@ def main():
                 "traffic": traffic, "peak_source": "148 SMs x 64 IMAD/clk x sm_max_mhz; tools/microbench measured 18.52 T IMAD/s and 9.12 T IMAD.WIDE/s (profiles/r01_microbench_imad.json)",
                 "algorithmic_imad_per_item": {k: 2 * v for k, v in wm.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_sum.items()},
+                "stage_frac_of_imad_peak": {"k_points": (2 * wm["points"] * B / (stage_sum["points"] / args.steps * 1e-3)) / imad_peak,
+                                            "k_ladders": achieved / imad_peak},
                 "pipeline_frac_of_imad_peak": (B * args.steps * 2 * wm["total"] / (dev_ms * 1e-3)) / imad_peak,
                 "pipeline_frac_at_observed_clock": ((B * args.steps * 2 * wm["total"] / (dev_ms * 1e-3)) / (148 * 64 * clk["sm_mhz"] * 1e6)) if clk.get("sm_mhz") else None,
                 "hbm": {"algorithmic_GBps": hbm_bytes * args.steps / (dev_ms * 1e-3) / 1e9, "peak_GBps": peaks.get("hbm_gbs", 6650.0),
