@@ -22,6 +22,9 @@
 
 namespace afx {
 
+#ifndef AFX_SYNC_MASK
+#define AFX_SYNC_MASK 0   // ladder CTAs re-align at a barrier every (AFX_SYNC_MASK + 1) windows
+#endif
 constexpr int MAX_ATTRS = 32;
 constexpr int MAX_VAR_TERMS = MAX_ATTRS + 4;
 constexpr int MAX_CONST_TERMS = MAX_ATTRS + 8;
@@ -345,9 +348,12 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
     ge acc = ge_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
-        AFX_STEP_SYNC();
+        if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
 #endif
         if (i != 63) ge_dbl4(acc);
+#if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
+        AFX_STEP_SYNC();
+#endif
         for (u32 k = 0; k < d.nvar; k++) {
             int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
             pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].atab_slot, item), dig);
@@ -426,9 +432,12 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
     ge acc = ge_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
-        AFX_STEP_SYNC();
+        if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
 #endif
         if (i != 63) ge_dbl4(acc);
+#if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
+        AFX_STEP_SYNC();
+#endif
         for (u32 k = 0; k < d.nvar; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
@@ -491,9 +500,12 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
     ge acc = ge_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
-        AFX_STEP_SYNC();
+        if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
 #endif
         if (i != 63) ge_dbl4(acc);
+#if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
+        AFX_STEP_SYNC();
+#endif
         for (u32 k = 0; k < d.nvar; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
