@@ -9,6 +9,7 @@
 // G_y padded to >= 3, singular/plural transcript labels, identity rejection only for allocated points).
 // Pure byte/bookkeeping work: no field arithmetic happens on the host.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstring>
 #include <stdexcept>
@@ -391,6 +392,12 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
     }
     P.n_msm = slot; P.n_proofs = (u32)P.txs.size();
     mark_comb_jobs(P);
+    if (!batchable) {   // longest point jobs first, so that the short ones fill the tail of the k_points grid (slots are already assigned)
+        auto cost = [](const PointJob& j) {
+            return 13 * (j.op == PJ_COPY ? 1 : 2) + ((j.table_slot >= 0 || j.atab_slot >= 0) ? 4 : 0) + 13 * ((j.comp_slot >= 0) + (j.compneg_slot >= 0));
+        };
+        std::stable_sort(P.point_jobs.begin(), P.point_jobs.end(), [&](const PointJob& a, const PointJob& b) { return cost(a) > cost(b); });
+    }
     if (batchable) {   // the same constraints as inputs of one random linear combination per chunk (engine.cuh, RLC section)
         RlcDesc R; std::memset(&R, 0, sizeof R);
         u32 ni = 0, nt = 0;
