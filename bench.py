@@ -434,7 +434,10 @@ def main():
         pass
     hbm_bytes = B * (WORDS * 32 + 1)
     roofline = {"bound": "imad", "kernel": "k_ladders", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": achieved / imad_peak,
-                "traffic": traffic, "peak_source": "148 SMs x 64 IMAD/clk x sm_max_mhz; tools/microbench measured 18.52 T IMAD/s and 9.12 T IMAD.WIDE/s (profiles/r01_microbench_imad.json)",
+                "traffic": traffic,
+                "traffic_note": "DRAM bytes of one k_ladders launch (ncu): ~25 GB are the aMAC ladder's constant-address table scans (every entry of "
+                                "every per-item table is read at every step so that no address depends on an issuer secret), the rest per-item "
+                                "ladder tables; 15 % of DRAM throughput, the kernel is bound by the IMAD pipe (fma-heavy 81 % busy)", "peak_source": "148 SMs x 64 IMAD/clk x sm_max_mhz; tools/microbench measured 18.52 T IMAD/s and 9.12 T IMAD.WIDE/s (profiles/r01_microbench_imad.json)",
                 "algorithmic_imad_per_item": {k: 2 * v for k, v in wm.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_sum.items()},
                 "stage_frac_of_imad_peak": {"k_points": (2 * wm["points"] * B / (stage_sum["points"] / args.steps * 1e-3)) / imad_peak,
