@@ -7,7 +7,8 @@
  * A batch entry point added beside each of those (Issuer::verify_batch, Issuer::issue_batch,
  * CredentialIssuance::verify_batch -- see INTEGRATION.md for the Rust shim) flattens its arguments to the plain
  * buffers below and binds exactly these symbols.  Plain pointers and sizes only; the caller owns every buffer; the
- * library copies what it keeps.  All functions are synchronous unless they take a stream.
+ * library copies what it keeps.  All functions are synchronous unless they take a stream.  A context is used by one thread at
+ * a time (it owns one workspace and its CUDA streams); replicate it per GPU and per concurrent caller.
  *
  * Batch data is struct-of-arrays: "field f" is an array [count][32 bytes].  A 32-byte word is either a canonical
  * little-endian Scalar or a CompressedRistretto -- the same encodings the reference's to_bytes() methods emit
@@ -47,11 +48,13 @@ enum { AFX_KIND_PUBLIC_SCALAR = 0, AFX_KIND_SECRET_SCALAR = 1, AFX_KIND_PUBLIC_P
 /* Replaces Issuer::from_bytes / holding an `Issuer` (src/issuer.rs:61-65,152-159).
  *   sysparams  = SystemParameters::to_bytes()   (src/parameters.rs:155-184)
  *   issuer_pub = C_W || I                        (the 64 bytes src/issuer.rs:155,163 reserve for IssuerParameters)
- *   secret     = amacs::SecretKey::to_bytes()    (src/amacs.rs:110-125); NULL for a user-side context that only runs
- *                afx_verify_issuances
+ *   secret     = amacs::SecretKey::to_bytes()    (src/amacs.rs:110-125); NULL for a user-side context, which runs
+ *                afx_verify_issuances* and afx_show* but neither afx_verify_presentations* nor afx_issue* (AFX_ERR_NO_SECRET)
  *   device     = CUDA device ordinal
  * Validates every encoding (AFX_ERR_ENCODING), builds the per-issuer constant tables and transcript midstates on the
- * device.  max_batch = largest `count` a single call will be given (workspace is sized for it). */
+ * device.  max_batch = number of items one device pass handles (the workspace is sized for it); host calls with a larger
+ * `count` are split into passes of max_batch items and pipelined (copy of pass i+1 under the kernels of pass i), the *_device
+ * calls take at most max_batch items. */
 int afx_ctx_create(const uint8_t* sysparams, size_t sysparams_len, const uint8_t issuer_pub[64], const uint8_t* secret,
                    size_t secret_len, int device, size_t max_batch, afx_ctx** out);
 
