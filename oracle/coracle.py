@@ -99,8 +99,8 @@ class Issuer:
             raise ValueError("bad issuer encoding")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().afxo_issuer_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:      # at interpreter shutdown the module globals may already be gone
+            _lib.afxo_issuer_free(self._h)
             self._h = None
 
     def synth(self, request_kinds: bytes, hide, config: bytes, start: int, count: int, threads: int = 0, want_issuances=True,
