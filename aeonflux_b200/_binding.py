@@ -30,7 +30,7 @@ class AfxError(RuntimeError):
 class Binding:
     SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
                "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
-               "afx_verify_issuances_device", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
+               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -50,6 +50,11 @@ class Binding:
         L.afx_verify_presentations_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp]
         L.afx_verify_issuances_device.restype = ctypes.c_int
         L.afx_verify_issuances_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp]
+        for f in ("afx_verify_presentations_submit", "afx_verify_issuances_submit"):
+            getattr(L, f).restype = ctypes.c_int
+            getattr(L, f).argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(ctypes.c_uint64)]
+        L.afx_wait.restype = ctypes.c_int
+        L.afx_wait.argtypes = [vp, ctypes.c_uint64]
         L.afx_batchable_num_fields.restype = sz
         L.afx_batchable_num_fields.argtypes = [ctypes.c_uint16, ctypes.c_char_p]
         L.afx_verify_presentations_batchable.restype = ctypes.c_int

@@ -175,6 +175,24 @@ class Issuer:
         """Batch Issuer::verify (issuer.rs:141-147): verdict 0 = Ok(()), 1 = Err(VerificationFailure)."""
         return self._run(self._b.L.afx_verify_presentations, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
 
+    def submit(self, batch: PresentationBatch, issuance=False):
+        """Asynchronous Issuer::verify (or CredentialIssuance::verify) of one pass (count <= max_batch): returns a pending result;
+        call .wait() for the verdicts.  Up to two submissions may be outstanding (copy of one under the kernels of the other)."""
+        ptrs, keep = B._as_fields(batch.fields)
+        cb = B.afx_presentation_batch(len(batch.kinds), batch.kinds, batch.count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        verdicts = np.zeros(batch.count, np.uint8)
+        ticket = ctypes.c_uint64(0)
+        fn = self._b.L.afx_verify_issuances_submit if issuance else self._b.L.afx_verify_presentations_submit
+        self._b.check(fn(self._h, ctypes.byref(cb), verdicts.ctypes.data, ctypes.byref(ticket)))
+        issuer = self
+
+        class Pending:
+            def wait(self_inner):
+                issuer._b.check(issuer._b.L.afx_wait(issuer._h, ticket.value))
+                return verdicts
+            _keep = (keep, ptrs, cb)
+        return Pending()
+
     def verify_batchable(self, batch: PresentationBatch, debug=False):
         """Batch Issuer::verify for presentations whose proofs are BatchableProofs (commitments instead of challenges, see
         include/aeonflux_b200.h): every constraint of every item is checked exactly."""

@@ -100,6 +100,15 @@ typedef struct {
 /* Batch CredentialIssuance::verify (src/issuer.rs:48-57 -> src/nizk/issuance.rs:132-218).  Needs no secret key. */
 int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
 
+/* Asynchronous host calls for a caller that streams batches (SURVEY 8b "optional async/stream variant"): submit enqueues the
+ * copy, the kernels and the verdict read-back of one pass (count <= max_batch) and returns a ticket; afx_wait(ticket) blocks until
+ * the verdicts are in the array given at submission.  Up to two submissions may be outstanding per context, so the copy of one
+ * overlaps the kernels of the other; a third submit, or any synchronous multi-pass call, while two are outstanding returns
+ * AFX_ERR_ARG.  The field buffers and the verdict array must stay valid until afx_wait returns. */
+int afx_verify_presentations_submit(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, uint64_t* ticket);
+int afx_verify_issuances_submit(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, uint64_t* ticket);
+int afx_wait(afx_ctx* ctx, uint64_t ticket);
+
 /* BatchableProof form (opt-in, NOT the reference's encoding).  The reference proves with zkp's CompactProof
  * (challenge + responses); its authors left zkp's BatchVerifier commented out (src/nizk/presentation.rs:33-34), which needs the
  * other zkp encoding, BatchableProof = blinding commitments + responses.  These entry points verify presentations whose proofs

@@ -368,3 +368,28 @@ def test_batchable_proofs_exact_and_rlc_on_gpu(readme4):
     v, fell_back = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, bp), bytes(range(32)))
     expect[bad[2:]] = 0
     assert (v == expect).all() and fell_back == 1
+
+
+def test_async_submit_wait_on_gpu(readme4):
+    """afx_verify_presentations_submit / afx_wait on the GPU: a stream of passes with two always in flight (the copy of one under
+    the kernels of the other); every verdict vector equals the oracle's."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    orc, _, (sp, ip, sk) = readme4
+    n_pass, per = 6, 4096
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"async-gpu", 0, 1024, want_issuances=False)
+    rng = np.random.default_rng(61)
+    items = pres[rng.integers(0, 1024, n_pass * per)].copy()
+    bad = rng.choice(n_pass * per, 40, replace=False)
+    for i in bad:
+        items[i, rng.integers(0, 28), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+    expect = np.zeros(n_pass * per, np.uint8); expect[bad] = 1
+    iss = Issuer(sp, ip, sk, device=0, max_batch=per)
+    batches = [PresentationBatch.from_items(kinds, items[k * per:(k + 1) * per]) for k in range(n_pass)]
+    pending, got = [], []
+    for b in batches:
+        if len(pending) == 2:
+            got.append(pending.pop(0).wait())
+        pending.append(iss.submit(b))
+    got += [p.wait() for p in pending]
+    assert (np.concatenate(got) == expect).all()
+    assert (iss.verify_batch(PresentationBatch.from_items(kinds, items)) == expect).all()     # and the synchronous path still works after it

@@ -344,3 +344,28 @@ def test_batchable_proofs_exact_and_rlc(emu, coracle, name):
     assert list(v) == expect
     vr, fell_back = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, bad), bytes(range(32)))
     assert list(vr) == expect and fell_back == 2                      # both chunks of 4 and 2 items hold a bad item
+
+
+def test_async_submit_wait(emu, coracle):
+    """afx_*_submit / afx_wait: two submissions in flight, waited in and out of order; a third is refused until one is waited."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from aeonflux_b200._binding import AfxError
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"async", 0, 12)
+    pres[2, 1, 0] ^= 1; pres[9, 5, 3] ^= 2
+    ov, _ = orc.verify_presentations(kinds, pres)
+    iss = Issuer(sp, ip, sk, max_batch=6, _binding=emu)
+    a = iss.submit(PresentationBatch.from_items(kinds, pres[:6]))
+    b = iss.submit(PresentationBatch.from_items(kinds, pres[6:]))
+    with pytest.raises(AfxError):
+        iss.submit(PresentationBatch.from_items(kinds, pres[:1]))
+    with pytest.raises(AfxError):
+        iss.verify_batch(PresentationBatch.from_items(kinds, pres))          # a multi-pass call needs the same buffers
+    assert (b.wait() == ov[6:]).all() and (a.wait() == ov[:6]).all()
+    with pytest.raises(AfxError):
+        a.wait()                                                             # a ticket is good for one wait
+    c = iss.submit(PresentationBatch.from_items(bytes([0, 0, 2, 2]), issu[:5]), issuance=True)
+    d = iss.submit(PresentationBatch.from_items(kinds, pres[:4]))
+    assert not c.wait().any() and (d.wait() == ov[:4]).all()
+    assert (iss.verify_batch(PresentationBatch.from_items(kinds, pres)) == ov).all()
