@@ -6,7 +6,7 @@ Parity status: the reference holds no golden vectors (all its tests draw from
 thread_rng) and cannot be compiled here (no Rust toolchain), so this
 oracle is pinned by external KATs for the third-party layers (see ristretto.py,
 merlin.py) and by reproducing the verdicts of the reference's own tests
-(tests/test_oracle_flows.py) -- "parity unpinned by the reference itself" at the byte
+(tests/test_oracle_kats.py::test_reference_test_verdicts) -- "parity unpinned by the reference itself" at the byte
 level, as DESIGN.md states.
 """
 import hashlib
