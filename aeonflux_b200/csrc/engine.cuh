@@ -345,12 +345,12 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
         sc_recode16(rec, sc_mul(y, m));
         for (int w = 0; w < 8; w++) scratch[(k * 8 + w) * scratch_stride] = rec[w];
     }
-    ge acc = ge_identity();
+    gc cacc = gc_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
         if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
 #endif
-        if (i != 63) ge_dbl4(acc);
+        if (i != 63) gc_dbl4(cacc);
 #if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
         AFX_STEP_SYNC();
 #endif
@@ -358,16 +358,17 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
             int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
             pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].atab_slot, item), dig);
             prefetch_atab(atab_ptr(ws, d.var[k + 1 < d.nvar ? k + 1 : 0].atab_slot, item & ~31u));   // next lookup, hidden behind this add
-            GE_LADDER_ADD(acc, e);
+            GE_LADDER_ADD(cacc, e);
         }
         for (u32 k = 0; k < d.nps; k++) {
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.ps[k].ctab * CTAB_ENTRIES * 24, dig);
-            GE_LADDER_MADD(acc, e);
+            GE_LADDER_MADD(cacc, e);
         }
     }
     for (u32 k = 0; k < d.nps * 8u; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded y_i * m_i
+    ge acc = gc_to_ge(cacc);
     // Z = (C_V - W) - acc
     ge cv = load_ge(ext_ptr(ws, d.ext_cv, item));
     ge z = ge_add_pn(cv, pniels_cneg(load_pniels(ws.W_pniels), 1));
@@ -399,7 +400,7 @@ struct CtabResolver {
 template <typename CtabOf>
 AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, CtabOf ctab_of, bool active = true) {
     if (d.flags & MSM_COMB) {      // constant bases only: radix-16 comb, public digits index it directly, no doublings
-        ge acc = ge_identity();
+        gc cacc = gc_identity();
         for (u32 k = 0; k < d.ncon; k++) {
             u32 rec[8];
             sc_recode16(rec, eval_scalar(ws, d.con[k].s, item));
@@ -410,12 +411,12 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                     u32 neg = ((u32)dig >> 31) ^ d.con[k].neg;
                     u32 mag = (u32)(dig < 0 ? -dig : dig);
                     aniels e = aniels_cneg(load_aniels(comb + ((size_t)i * COMB_ENTRIES + (mag - 1)) * 24), neg);
-                    GE_LADDER_MADD(acc, e);
+                    GE_LADDER_MADD(cacc, e);
                 }
             }
         }
         u32 w[8];
-        ge_compress(w, acc);
+        ge_compress(w, gc_to_ge(cacc));
         if (active) store8(commit_ptr(ws, d.out_slot, item), w);
         return;
     }
@@ -429,12 +430,12 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
         sc_recode256(rec, eval_scalar(ws, d.con[k].s, item));
         for (int w = 0; w < 8; w++) scratch[((d.nvar + k) * 8 + w) * scratch_stride] = rec[w];
     }
-    ge acc = ge_identity();
+    gc cacc = gc_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
         if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
 #endif
-        if (i != 63) ge_dbl4(acc);
+        if (i != 63) gc_dbl4(cacc);
 #if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
         AFX_STEP_SYNC();
 #endif
@@ -446,7 +447,7 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                 u32 mag = (u32)(dig < 0 ? -dig : dig);
                 pniels e = load_pniels(table_ptr(ws, d.var[k].table_slot, item) + 32 * (mag - 1));
                 e = pniels_cneg(e, neg);
-                GE_LADDER_ADD(acc, e);
+                GE_LADDER_ADD(cacc, e);
             }
         }
         if ((i & 1) == 0) {
@@ -458,13 +459,13 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                     u32 mag = (u32)(dig < 0 ? -dig : dig);
                     aniels e = load_aniels(ctab_of(k) + 24 * (mag - 1));
                     e = aniels_cneg(e, neg);
-                    GE_LADDER_MADD(acc, e);
+                    GE_LADDER_MADD(cacc, e);
                 }
             }
         }
     }
     u32 w[8];
-    ge_compress(w, acc);
+    ge_compress(w, gc_to_ge(cacc));
     if (active) store8(commit_ptr(ws, d.out_slot, item), w);
 }
 
@@ -475,17 +476,18 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
 // zkp prove_compact).  scratch: (nvar + ncon) * 8 words per item.
 AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, bool active = true) {
     if (d.flags & MSM_COMB) {      // constant bases only: radix-16 comb with constant-address scans, no doublings
-        ge acc = ge_identity();
+        gc cacc = gc_identity();
         for (u32 k = 0; k < d.ncon; k++) {
             u32 rec[8];
             sc_recode16(rec, eval_scalar(ws, d.con[k].s, item));
             const u32* comb = ws.comb + (size_t)d.con[k].ctab * COMB_WINDOWS * COMB_ENTRIES * 24;
             for (int i = 0; i < COMB_WINDOWS; i++) {
                 aniels e = aniels_scan_select8(comb + (size_t)i * COMB_ENTRIES * 24, sc_digit16(rec, i), d.con[k].neg);
-                GE_LADDER_MADD(acc, e);
+                GE_LADDER_MADD(cacc, e);
             }
             for (int i = 0; i < 8; i++) rec[i] = 0;
         }
+        ge acc = gc_to_ge(cacc);
         if (d.flags & MSM_ADD_EXT) acc = ge_add(acc, load_ge(ext_ptr(ws, d.add_ext, item)));
         u32 w[8];
         ge_compress(w, acc);
@@ -497,12 +499,12 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
         sc_recode16(rec, eval_scalar(ws, k < d.nvar ? d.var[k].s : d.con[k - d.nvar].s, item));
         for (int w = 0; w < 8; w++) scratch[(k * 8 + w) * scratch_stride] = rec[w];
     }
-    ge acc = ge_identity();
+    gc cacc = gc_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
         if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
 #endif
-        if (i != 63) ge_dbl4(acc);
+        if (i != 63) gc_dbl4(cacc);
 #if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
         AFX_STEP_SYNC();
 #endif
@@ -510,16 +512,17 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].table_slot, item), dig, d.var[k].neg);
-            GE_LADDER_ADD(acc, e);
+            GE_LADDER_ADD(cacc, e);
         }
         for (u32 k = 0; k < d.ncon; k++) {
             u32 word = scratch[((d.nvar + k) * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.con[k].ctab * CTAB_ENTRIES * 24, dig, d.con[k].neg);
-            GE_LADDER_MADD(acc, e);
+            GE_LADDER_MADD(cacc, e);
         }
     }
     for (u32 k = 0; k < ((u32)d.nvar + d.ncon) * 8; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded secrets
+    ge acc = gc_to_ge(cacc);
     if (d.flags & MSM_ADD_W) acc = ge_add_pn(acc, load_pniels(ws.W_pniels));
     if (d.flags & MSM_ADD_EXT) acc = ge_add(acc, load_ge(ext_ptr(ws, d.add_ext, item)));
     u32 w[8];

@@ -67,21 +67,54 @@ AFX_HD ge ge_dbl_inl(const ge& p, bool need_T = true) {
     return r;
 }
 AFX_NI ge ge_dbl(ge p, bool need_T = true) { return ge_dbl_inl(p, need_T); }
-// Ladder-loop forms.  By default the window body is inlined into the (rolled) ladder loop, so the accumulator never
-// crosses a call boundary (no argument/return register shuffles: 23.7 -> 23.0 ms for k_ladders on B200);
-// -DAFX_LADDER_CALLS calls the __noinline__ subroutines instead.
-#if defined(__CUDA_ARCH__) && !defined(AFX_LADDER_CALLS)
-AFX_HD void ge_dbl4(ge& acc) {
-#pragma unroll 1
-    for (int j = 0; j < 4; j++) acc = ge_dbl_inl(acc, j == 3);
+// Ladder accumulator in "completed" coordinates (E, F, G, H): X = E*F, Y = G*H, Z = F*G, T = E*H.  Every ladder
+// operation starts by forming only the products it reads -- a doubling X, Y, Z (3M), an addition X, Y, Z, T (4M) -- so
+// T is never computed for a point that is doubled next: doubling 4S + 3M, add 4M + 4M, mixed add 4M + 3M, with no
+// data-dependent choice anywhere (the rolled 4-doubling loop body is uniform).  One multiply fewer per doubling than
+// carrying (X, Y, Z, T) through the rolled loop, where ptxas computes T in every iteration and selects.
+struct gc { fe E, F, G, H; };
+AFX_HD gc gc_identity() { gc r; r.E = fe_zero(); r.F = fe_one(); r.G = fe_one(); r.H = fe_one(); return r; }
+AFX_HD ge gc_to_ge(const gc& c) {
+    ge r; r.X = fe_mul(c.E, c.F); r.Y = fe_mul(c.G, c.H); r.Z = fe_mul(c.F, c.G); r.T = fe_mul(c.E, c.H); return r;
 }
-#define GE_LADDER_ADD(acc, e) acc = ge_add_pn_inl(acc, e, true)
-#define GE_LADDER_MADD(acc, e) acc = ge_madd_inl(acc, e, true)
-#else
-AFX_HD void ge_dbl4(ge& acc) { acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, false); acc = ge_dbl(acc, true); }
-#define GE_LADDER_ADD(acc, e) acc = ge_add_pn(acc, e, true)
-#define GE_LADDER_MADD(acc, e) acc = ge_madd(acc, e, true)
+AFX_HD gc gc_dbl_inl(const gc& c) {
+    fe X = fe_mul(c.E, c.F), Y = fe_mul(c.G, c.H), Z = fe_mul(c.F, c.G);
+    fe XX = fe_sq(X), YY = fe_sq(Y), ZZ = fe_sq(Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    fe S = fe_sq(fe_add(X, Y));
+    gc r; r.H = fe_add(YY, XX); r.G = fe_sub(YY, XX); r.E = fe_sub(S, r.H); r.F = fe_sub(ZZ2, r.G);
+    return r;
+}
+AFX_HD gc gc_add_pn_inl(const gc& c, const pniels& n) {
+    fe X = fe_mul(c.E, c.F), Y = fe_mul(c.G, c.H);
+    fe PP = fe_mul(fe_add(Y, X), n.YpX);
+    fe MM = fe_mul(fe_sub(Y, X), n.YmX);
+    fe TT = fe_mul(fe_mul(c.E, c.H), n.T2d);
+    fe ZZ = fe_mul(fe_mul(c.F, c.G), n.Z);
+    fe ZZ2 = fe_add(ZZ, ZZ);
+    gc r; r.E = fe_sub(PP, MM); r.H = fe_add(PP, MM); r.G = fe_add(ZZ2, TT); r.F = fe_sub(ZZ2, TT);
+    return r;
+}
+AFX_HD gc gc_madd_inl(const gc& c, const aniels& n) {
+    fe X = fe_mul(c.E, c.F), Y = fe_mul(c.G, c.H);
+    fe PP = fe_mul(fe_add(Y, X), n.ypx);
+    fe MM = fe_mul(fe_sub(Y, X), n.ymx);
+    fe TT = fe_mul(fe_mul(c.E, c.H), n.xy2d);
+    fe Z = fe_mul(c.F, c.G);
+    fe ZZ2 = fe_add(Z, Z);
+    gc r; r.E = fe_sub(PP, MM); r.H = fe_add(PP, MM); r.G = fe_add(ZZ2, TT); r.F = fe_sub(ZZ2, TT);
+    return r;
+}
+// Ladder-loop forms.  On the device the window body is inlined into the (rolled) ladder loop, so the accumulator never
+// crosses a call boundary (no argument/return register shuffles: 23.7 -> 23.0 ms for k_ladders on B200).
+AFX_HD void gc_dbl4(gc& acc) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
 #endif
+    for (int j = 0; j < 4; j++) acc = gc_dbl_inl(acc);
+}
+#define GE_LADDER_ADD(acc, e) acc = gc_add_pn_inl(acc, e)
+#define GE_LADDER_MADD(acc, e) acc = gc_madd_inl(acc, e)
 AFX_HD ge ge_add(const ge& p, const ge& q) { return ge_add_pn(p, ge_to_pniels(q)); }
 AFX_HD ge ge_sub(const ge& p, const ge& q) { return ge_add_pn(p, pniels_cneg(ge_to_pniels(q), 1)); }
 
