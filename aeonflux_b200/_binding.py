@@ -30,7 +30,7 @@ class AfxError(RuntimeError):
 class Binding:
     SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
                "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
-               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
+               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_host_alloc", "afx_host_free", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -55,6 +55,10 @@ class Binding:
             getattr(L, f).argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(ctypes.c_uint64)]
         L.afx_wait.restype = ctypes.c_int
         L.afx_wait.argtypes = [vp, ctypes.c_uint64]
+        L.afx_host_alloc.restype = ctypes.c_int
+        L.afx_host_alloc.argtypes = [ctypes.POINTER(vp), sz]
+        L.afx_host_free.restype = None
+        L.afx_host_free.argtypes = [vp]
         L.afx_batchable_num_fields.restype = sz
         L.afx_batchable_num_fields.argtypes = [ctypes.c_uint16, ctypes.c_char_p]
         L.afx_verify_presentations_batchable.restype = ctypes.c_int
@@ -96,6 +100,16 @@ class Binding:
 
     def version(self):
         return self.L.afx_version().decode()
+
+    def host_array(self, shape):
+        """uint8 ndarray of `shape` in page-locked host memory (afx_host_alloc), freed when the array is collected."""
+        import weakref
+        n = int(np.prod(shape))
+        p = ctypes.c_void_p()
+        self.check(self.L.afx_host_alloc(ctypes.byref(p), n))
+        buf = (ctypes.c_uint8 * max(n, 1)).from_address(p.value)
+        weakref.finalize(buf, self.L.afx_host_free, p.value)
+        return np.frombuffer(buf, dtype=np.uint8, count=n).reshape(shape)
 
 
 def _as_fields(fields):

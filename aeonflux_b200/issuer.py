@@ -43,9 +43,16 @@ class PresentationBatch:
         return self.fields.shape[1]
 
     @staticmethod
-    def from_items(kinds, items):
-        """items: uint8 [count][n_fields][32] (item-major, as a list of per-presentation word lists)."""
-        return PresentationBatch(kinds, np.ascontiguousarray(np.asarray(items, dtype=np.uint8).transpose(1, 0, 2)))
+    def from_items(kinds, items, host_array=None):
+        """items: uint8 [count][n_fields][32] (item-major, as a list of per-presentation word lists).  host_array: an allocator
+        such as Issuer.host_array -- the struct-of-arrays copy is then built in page-locked memory (afx_host_alloc), from which
+        the library's host-to-device copies run asynchronously at the full bus rate."""
+        items = np.asarray(items, dtype=np.uint8)
+        if host_array is None:
+            return PresentationBatch(kinds, np.ascontiguousarray(items.transpose(1, 0, 2)))
+        fields = host_array((items.shape[1], items.shape[0], 32))
+        fields[:] = items.transpose(1, 0, 2)
+        return PresentationBatch(kinds, fields)
 
 
 def compact_to_batchable(kinds, fields, commitments):
@@ -132,6 +139,10 @@ class Issuer:
     __del__ = close
 
     # -- shape helpers
+    def host_array(self, shape):
+        """uint8 ndarray in page-locked host memory (afx_host_alloc / afx_host_free)."""
+        return self._b.host_array(shape)
+
     def num_fields(self, kinds):
         return self._b.L.afx_presentation_num_fields(len(kinds), bytes(kinds))
 

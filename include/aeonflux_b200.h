@@ -109,6 +109,14 @@ int afx_verify_presentations_submit(afx_ctx* ctx, const afx_presentation_batch* 
 int afx_verify_issuances_submit(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, uint64_t* ticket);
 int afx_wait(afx_ctx* ctx, uint64_t ticket);
 
+/* Page-locked host memory for batch buffers (optional: every entry point accepts any host memory).  A host-to-device copy
+ * from page-locked memory runs at the full bus rate and asynchronously; from pageable memory the driver stages it at a
+ * fraction of that rate on the calling thread, which exposes the copy of every pass of a multi-pass call (S16: 300 MB per
+ * 65,536 items).  A shim that flattens its presentations into struct-of-arrays buffers should build them here.  The memory is
+ * not tied to a context; free it with afx_host_free (NULL is ignored). */
+int afx_host_alloc(void** out, size_t bytes);
+void afx_host_free(void* p);
+
 /* BatchableProof form (opt-in, NOT the reference's encoding).  The reference proves with zkp's CompactProof
  * (challenge + responses); its authors left zkp's BatchVerifier commented out (src/nizk/presentation.rs:33-34), which needs the
  * other zkp encoding, BatchableProof = blinding commitments + responses.  These entry points verify presentations whose proofs

@@ -51,7 +51,43 @@ extern "C" {
                                      verdicts: *mut u8) -> c_int;
     pub fn afx_issue(ctx: *mut afx_ctx, batch: *const afx_batch, out: *const afx_out, status: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
     pub fn afx_show(ctx: *mut afx_ctx, batch: *const afx_batch, out: *const afx_out, status: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
+    pub fn afx_verify_presentations_submit(ctx: *mut afx_ctx, batch: *const afx_batch, verdicts: *mut u8, ticket: *mut u64) -> c_int;
+    pub fn afx_wait(ctx: *mut afx_ctx, ticket: u64) -> c_int;
+    pub fn afx_host_alloc(out: *mut *mut std::os::raw::c_void, bytes: usize) -> c_int;
+    pub fn afx_host_free(p: *mut std::os::raw::c_void);
     pub fn afx_strerror(code: c_int) -> *const c_char;
+}
+
+/// A byte buffer in page-locked host memory (`afx_host_alloc`).  Build the struct-of-arrays fields of a batch in these:
+/// the library's host-to-device copies then run asynchronously at the full bus rate instead of being staged by the driver.
+pub struct PinnedBytes {
+    ptr: *mut u8,
+    len: usize,
+}
+
+unsafe impl Send for PinnedBytes {}
+
+impl PinnedBytes {
+    pub fn new(len: usize) -> Result<PinnedBytes, B200Error> {
+        let mut p: *mut std::os::raw::c_void = std::ptr::null_mut();
+        let rc = unsafe { afx_host_alloc(&mut p, len) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        unsafe { std::ptr::write_bytes(p as *mut u8, 0, len) };
+        Ok(PinnedBytes { ptr: p as *mut u8, len })
+    }
+}
+
+impl std::ops::Deref for PinnedBytes {
+    type Target = [u8];
+    fn deref(&self) -> &[u8] { unsafe { std::slice::from_raw_parts(self.ptr, self.len) } }
+}
+
+impl std::ops::DerefMut for PinnedBytes {
+    fn deref_mut(&mut self) -> &mut [u8] { unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) } }
+}
+
+impl Drop for PinnedBytes {
+    fn drop(&mut self) { unsafe { afx_host_free(self.ptr as *mut std::os::raw::c_void) } }
 }
 
 /// A non-zero return code of the C ABI (`AFX_ERR_*`).
@@ -105,6 +141,29 @@ impl B200Context {
         let rc = unsafe { afx_verify_presentations(self.ctx, &batch, verdicts.as_mut_ptr(), std::ptr::null_mut()) };
         if rc != 0 { return Err(B200Error(rc)); }
         Ok(verdicts)
+    }
+
+    /// Asynchronous `Issuer::verify` of one pass (`count <= max_batch`): enqueues the copy, the kernels and the verdict
+    /// read-back and returns a ticket for `wait`.  Two submissions may be outstanding, so the copy of one runs under the
+    /// kernels of the other.  `fields` and `verdicts` must stay alive and untouched until `wait(ticket)` returns -- hence
+    /// `unsafe`; a safe wrapper would own both in the returned handle.
+    pub unsafe fn submit_presentations(&self, kinds: &[u8], fields: &[&[u8]], verdicts: &mut [u8]) -> Result<u64, B200Error> {
+        let n_fields = afx_presentation_num_fields(kinds.len() as u16, kinds.as_ptr());
+        let count = Self::check_fields(fields, n_fields)?;
+        if verdicts.len() != count { return Err(B200Error(-1)); }
+        let ptrs: Vec<*const u8> = fields.iter().map(|f| f.as_ptr()).collect();
+        let batch = afx_batch { n_attrs: kinds.len() as u16, kinds: kinds.as_ptr(), count, fields: ptrs.as_ptr(), n_fields };
+        let mut ticket = 0u64;
+        let rc = afx_verify_presentations_submit(self.ctx, &batch, verdicts.as_mut_ptr(), &mut ticket);
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(ticket)
+    }
+
+    /// Blocks until the submission's verdicts are in the array given to `submit_presentations`.
+    pub fn wait(&self, ticket: u64) -> Result<(), B200Error> {
+        let rc = unsafe { afx_wait(self.ctx, ticket) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(())
     }
 
     /// Batch `Issuer::verify` over item-major wire bytes (`count * n_fields * 32` bytes, as received).

@@ -369,3 +369,25 @@ def test_async_submit_wait(emu, coracle):
     d = iss.submit(PresentationBatch.from_items(kinds, pres[:4]))
     assert not c.wait().any() and (d.wait() == ov[:4]).all()
     assert (iss.verify_batch(PresentationBatch.from_items(kinds, pres)) == ov).all()
+
+
+def test_host_alloc_buffers(emu, coracle):
+    """afx_host_alloc / afx_host_free: a batch built in library-allocated host memory verifies like any other; freeing NULL is a
+    no-op and a NULL out pointer is an argument error."""
+    import gc
+    from aeonflux_b200 import Issuer, PresentationBatch
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"hostalloc", 0, 5)
+    pres[3, 2, 9] ^= 8
+    ov, _ = orc.verify_presentations(kinds, pres)
+    iss = Issuer(sp, ip, sk, max_batch=4, _binding=emu)
+    batch = PresentationBatch.from_items(kinds, pres, host_array=iss.host_array)
+    assert batch.fields.shape == (28, 5, 32) and (batch.fields.transpose(1, 0, 2) == pres).all()
+    assert (iss.verify_batch(batch) == ov).all() and list(ov) == [0, 0, 0, 1, 0]
+    del batch
+    gc.collect()                                     # runs afx_host_free through the finalizer
+    assert emu.L.afx_host_alloc(None, 16) != 0
+    emu.L.afx_host_free(None)
+    z = iss.host_array((0, 32))
+    assert z.shape == (0, 32)
