@@ -384,7 +384,8 @@ def test_async_submit_wait_on_gpu(readme4):
         items[i, rng.integers(0, 28), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
     expect = np.zeros(n_pass * per, np.uint8); expect[bad] = 1
     iss = Issuer(sp, ip, sk, device=0, max_batch=per)
-    batches = [PresentationBatch.from_items(kinds, items[k * per:(k + 1) * per]) for k in range(n_pass)]
+    # odd passes are staged in page-locked memory from the library's allocator (afx_host_alloc), even ones in numpy memory
+    batches = [PresentationBatch.from_items(kinds, items[k * per:(k + 1) * per], host_array=iss.host_array if k % 2 else None) for k in range(n_pass)]
     pending, got = [], []
     for b in batches:
         if len(pending) == 2:
