@@ -842,13 +842,19 @@ AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words
 }
 
 // ---- primitive self-test (parity hooks for the field / group / scalar code, independent of the protocol flows) ------
-enum : u32 { PRIM_DECOMPRESS_COMPRESS = 0, PRIM_FROM_UNIFORM = 1, PRIM_SCALARMULT = 2, PRIM_WIDE_REDUCE = 3, PRIM_SC_MULADD = 4 };
+enum : u32 { PRIM_DECOMPRESS_COMPRESS = 0, PRIM_FROM_UNIFORM = 1, PRIM_SCALARMULT = 2, PRIM_WIDE_REDUCE = 3, PRIM_SC_MULADD = 4,
+             PRIM_FE_MUL = 5, PRIM_FE_SQ = 6, PRIM_FE_ADD = 7, PRIM_FE_SUB = 8, PRIM_FE_CHAIN = 9, PRIM_LADDER_STEP = 10 };
 // in/out are [count][words][8] item-major.  Returns per item ok (1) / rejected encoding (0) in flags.
 //   0: in 1 word (encoding)          -> out 1 word: compress(decompress(in)); flag = decodes
 //   1: in 2 words (64 uniform bytes) -> out 1 word: compress(from_uniform_bytes(in))
 //   2: in 2 words (scalar, encoding) -> out 1 word: compress(scalar * point)  (fixed-window ladder over the [1P..8P] table)
 //   3: in 2 words (64 bytes)         -> out 1 word: the integer mod l
 //   4: in 3 words (a, b, c)          -> out 1 word: a*b + c mod l
+//   5..8: in 2 words (a, b: raw 256-bit limb vectors, NOT reduced -- any value in [0, 2^256) is a legal lazily-reduced
+//         field element) -> out 1 word: canonical bytes of a*b, a^2, a+b, a-b mod p
+//   9: in 2 words (a, b raw)         -> out 1 word: canonical ((a+b)*(a-b))^2 * (a-b) + a  (unreduced intermediates chained)
+//  10: in 2 words (scalar, encoding) -> out 1 word: compress(scalar * point) through the completed-coordinates ladder forms
+//         (gc_dbl4 / gc_add_pn_inl / gc_to_ge) that k_ladders and k_msm_ct use
 AFX_HD void primitive_job(u32 op, const u32* in, u32* out, u32* flags, u32 item) {
     u32 w[8]; u32 ok = 1;
     if (op == PRIM_DECOMPRESS_COMPRESS) {
@@ -874,6 +880,30 @@ AFX_HD void primitive_job(u32 op, const u32* in, u32* out, u32* flags, u32 item)
     } else if (op == PRIM_WIDE_REDUCE) {
         sc r = sc_reduce512(in + (size_t)item * 16);
         for (int i = 0; i < 8; i++) w[i] = r.v[i];
+    } else if (op >= PRIM_FE_MUL && op <= PRIM_FE_CHAIN) {
+        fe a, b, r;
+        for (int i = 0; i < 8; i++) { a.v[i] = in[(size_t)item * 16 + i]; b.v[i] = in[(size_t)item * 16 + 8 + i]; }
+        if (op == PRIM_FE_MUL) r = fe_mul(a, b);
+        else if (op == PRIM_FE_SQ) r = fe_sq(a);
+        else if (op == PRIM_FE_ADD) r = fe_add(a, b);
+        else if (op == PRIM_FE_SUB) r = fe_sub(a, b);
+        else { fe d = fe_sub(a, b); r = fe_add(fe_mul(fe_sq(fe_mul(fe_add(a, b), d)), d), a); }
+        fe_to_bytes_words(w, r);
+    } else if (op == PRIM_LADDER_STEP) {
+        ge p; ok = ge_decompress(p, in + (size_t)item * 16 + 8);
+        sc s = sc_from_words(in + (size_t)item * 16);
+        ok &= sc_is_canonical(s);
+        u32 rec[8]; sc_recode16(rec, s);
+        pniels tab[8];
+        struct Keep { pniels* t; AFX_HD void operator()(int e, const pniels& n) const { t[e] = n; } };
+        Keep keep{tab}; ge_table8(p, keep);
+        gc cacc = gc_identity();
+        for (int i = 63; i >= 0; i--) {
+            if (i != 63) gc_dbl4(cacc);
+            int dig = sc_digit16(rec, i);
+            if (dig != 0) { u32 mag = (u32)(dig < 0 ? -dig : dig); pniels e = pniels_cneg(tab[mag - 1], (u32)dig >> 31); GE_LADDER_ADD(cacc, e); }
+        }
+        ge_compress(w, gc_to_ge(cacc));
     } else {
         const u32* q = in + (size_t)item * 24;
         sc r = sc_muladd(sc_from_words(q), sc_from_words(q + 8), sc_from_words(q + 16));

@@ -214,7 +214,11 @@ int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t
  *   op 1: in [count][64] uniform bytes          -> compress(from_uniform_bytes(in))   (RistrettoPoint::from_uniform_bytes)
  *   op 2: in [count][2][32] scalar, encoding    -> compress(scalar * point)
  *   op 3: in [count][64] bytes                  -> the integer mod l                  (Scalar::from_bytes_mod_order_wide)
- *   op 4: in [count][3][32] scalars a, b, c     -> a*b + c mod l */
+ *   op 4: in [count][3][32] scalars a, b, c     -> a*b + c mod l
+ *   op 5..8: in [count][2][32] raw 256-bit limb vectors a, b (any value in [0, 2^256) is a legal lazily reduced field element)
+ *                                               -> canonical bytes of a*b, a^2, a+b, a-b mod 2^255-19
+ *   op 9: same inputs                           -> canonical ((a+b)(a-b))^2 (a-b) + a     (chained unreduced intermediates)
+ *   op 10: in [count][2][32] scalar, encoding   -> compress(scalar * point) through the completed-coordinates ladder forms */
 int afx_selftest_primitive(afx_ctx* ctx, int op, const uint8_t* in, size_t count, uint8_t* out, uint8_t* ok);
 
 /* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */

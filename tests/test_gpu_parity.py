@@ -321,10 +321,11 @@ def test_show_full_size_round_trip(readme4):
 def test_primitives_on_gpu(coracle):
     """Field / group / scalar primitives of the CUDA engine against the committed primitive vectors and the C oracle."""
     from aeonflux_b200 import Issuer
-    from tests.test_host_logic import check_primitives
+    from tests.test_host_logic import check_field_edges, check_primitives
     sp, ip, sk = coracle.make_issuer(1)
     iss = Issuer(sp, ip, None, device=0, max_batch=4)
     check_primitives(iss, coracle)
+    check_field_edges(iss, n_random=100000)            # the PTX carry chains on edge-limb vectors (the emulation has plain C there)
     # 20,000 random 32-byte strings: the decode verdicts equal the oracle's (about 6.8 % decode), valid ones round-trip
     rng = np.random.default_rng(18)
     enc = rng.integers(0, 256, (20000, 32), dtype=np.uint8)

@@ -297,6 +297,35 @@ def check_primitives(iss, coracle):
         assert (got[i] == exp).all()
         L.afxo_sc_muladd(abc[i, :32].ctypes.data, abc[i, 32:64].ctypes.data, abc[i, 64:].ctypes.data, exp.ctypes.data)
         assert (got2[i] == exp).all()
+    # the ladder forms k_ladders / k_msm_ct use (completed coordinates) against the plain extended-coordinates ladder and the oracle
+    got3, ok3 = iss.selftest_primitive("ladder_scalarmult", np.concatenate([scal, pts], axis=1))
+    got, ok = iss.selftest_primitive("scalarmult", np.concatenate([scal, pts], axis=1))
+    assert ok3.all() and (got3 == got).all()
+    check_field_edges(iss)
+
+
+def check_field_edges(iss, n_random=3000):
+    """fe_mul / fe_sq / fe_add / fe_sub on raw 256-bit limb vectors -- every value in [0, 2^256) is a legal lazily reduced
+    element -- against Python integers: hand-picked extremes (0, 1, p-1, p, p+1, 2p, 2p+1 .. 2^256-1, 2^255, 38-multiples) in all
+    pairs, and vectors whose limbs are drawn from edge words (0, 1, 2^32-1, 2^32-38, ...), which is where the carry folds of
+    the device code (and nowhere else) take their rare paths."""
+    P = 2**255 - 19
+    M = 2**256
+    special = [0, 1, 2, 18, 19, 37, 38, 39, P - 1, P, P + 1, P + 18, P + 19, 2 * P - 1, 2 * P, 2 * P + 1, M - 39, M - 38, M - 37, M - 2, M - 1,
+               2**255, 2**255 - 1, 2**255 + 18, 2**128, 2**128 - 1, M - 2**128, M - 2**32, 2**32 - 1, 2**32, (M - 1) // 3, (M - 1) // 38]
+    rng = np.random.default_rng(23)
+    words = np.array([0, 1, 2, 37, 38, 0x7fffffff, 0x80000000, 0xfffffffe, 0xffffffff, 0xffffffda, 0xffffffd9, 0xffffffed, 0x0000ffff, 0xffff0000], np.uint64)
+    vals = [(a, b) for a in special for b in special]
+    for _ in range(n_random):
+        pick = lambda: sum(int(words[rng.integers(0, len(words))]) << (32 * i) for i in range(8)) if rng.random() < 0.7 else int.from_bytes(rng.bytes(32), "little")
+        vals.append((pick(), pick()))
+    inp = np.frombuffer(b"".join(a.to_bytes(32, "little") + b.to_bytes(32, "little") for a, b in vals), np.uint8).reshape(-1, 64)
+    for name, f in (("fe_mul", lambda a, b: a * b), ("fe_sq", lambda a, b: a * a), ("fe_add", lambda a, b: a + b), ("fe_sub", lambda a, b: a - b),
+                    ("fe_chain", lambda a, b: ((a + b) * (a - b)) ** 2 * (a - b) + a)):
+        out, _ = iss.selftest_primitive(name, inp)
+        exp = np.frombuffer(b"".join((f(a, b) % P).to_bytes(32, "little") for a, b in vals), np.uint8).reshape(-1, 32)
+        bad = np.nonzero((out != exp).any(axis=1))[0]
+        assert len(bad) == 0, (name, [hex(v) for v in vals[bad[0]]])
 
 
 def test_primitives_on_emulation(emu, coracle):
