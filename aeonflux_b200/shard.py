@@ -108,3 +108,47 @@ class ShardedIssuer:
                 local = issuer.verify_batch(PresentationBatch(kinds, fields[:, lo:hi])) if hi > lo else np.zeros(0, np.uint8)
                 out[sel] = self._gather_bitmaps(pack_bitmap(local), len(sel))
         return out
+
+
+class MultiGpuIssuer:
+    """ONE process driving several B200s: a replicated `Issuer` context per device and one host thread per context (SURVEY 8e:
+    "one thread + stream set per GPU").  This is the form a single-process caller -- the reference is a library, its
+    `Issuer::verify_batch` shim runs inside the application -- uses instead of one process per GPU; the partition is the same
+    (contiguous item slices, no data-path communication, verdicts concatenated).  The C ABI is thread-compatible across contexts:
+    each context owns its streams, workspace and shape cache, and every call selects its device first; ctypes releases the GIL
+    for the duration of a call, so the device passes run concurrently."""
+
+    def __init__(self, system_parameters, issuer_parameters, amacs_key=None, devices=(0,), max_batch=65536, _binding=None):
+        from concurrent.futures import ThreadPoolExecutor
+        from .issuer import Issuer
+        if not devices:
+            raise ValueError("at least one device")
+        self.devices = list(devices)
+        self.issuers = [Issuer(system_parameters, issuer_parameters, amacs_key, device=d, max_batch=max_batch, _binding=_binding) for d in self.devices]
+        self._pool = ThreadPoolExecutor(max_workers=len(self.devices))
+
+    def host_array(self, shape):
+        return self.issuers[0].host_array(shape)
+
+    def _fan_out(self, method, batch):
+        g = len(self.issuers)
+        if batch.count == 0:
+            return np.zeros(0, np.uint8)
+        jobs = []
+        for k, iss in enumerate(self.issuers):
+            lo, hi = slice_bounds(batch.count, k, g)
+            if hi > lo:
+                jobs.append(self._pool.submit(getattr(iss, method), PresentationBatch(batch.kinds, batch.fields[:, lo:hi])))
+        return np.concatenate([j.result() for j in jobs])
+
+    def verify_batch(self, batch: PresentationBatch) -> np.ndarray:
+        """Batch Issuer::verify: device k verifies items [k*N/G, (k+1)*N/G); verdicts in item order."""
+        return self._fan_out("verify_batch", batch)
+
+    def verify_issuance_batch(self, batch: PresentationBatch) -> np.ndarray:
+        return self._fan_out("verify_issuance_batch", batch)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for iss in self.issuers:
+            iss.close()

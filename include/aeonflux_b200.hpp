@@ -25,6 +25,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -185,6 +186,45 @@ private:
     std::vector<uint8_t> sp_, ip_, sk_;
     afx_ctx* ctx_ = nullptr;
     friend struct CredentialIssuance;
+    friend class MultiGpuIssuer;
+};
+
+// One process driving several B200s: a replicated context per device and one host thread per context ("one
+// thread + stream set per GPU").  Device k verifies the contiguous item slice [k*N/G, (k+1)*N/G); nothing but the verdicts is
+// gathered.  The single-process counterpart of bench.py's one-process-per-GPU launch.
+class MultiGpuIssuer {
+public:
+    MultiGpuIssuer(const std::vector<uint8_t>& system_parameters, const std::vector<uint8_t>& issuer_parameters, const std::vector<uint8_t>& amacs_key,
+                   const std::vector<int>& devices, size_t max_batch = 65536) {
+        if (devices.empty()) throw std::invalid_argument("at least one device");
+        issuers_.reserve(devices.size());
+        for (int d : devices) issuers_.emplace_back(system_parameters, issuer_parameters, amacs_key, d, max_batch);
+    }
+    size_t devices() const { return issuers_.size(); }
+    std::vector<Result<>> verify_batch(const PresentationBatch& p) const {
+        if (p.fields.size() != afx_presentation_num_fields((uint16_t)p.kinds.size(), p.kinds.data())) throw std::invalid_argument("wrong number of presentation fields");
+        p.pointers();   // rejects a ragged batch
+        const size_t g = issuers_.size(), n = p.count();
+        std::vector<uint8_t> v(n);
+        std::vector<int> rc(g, AFX_OK);
+        std::vector<std::thread> threads;
+        for (size_t k = 0; k < g; k++) {
+            const size_t lo = k * n / g, hi = (k + 1) * n / g;
+            if (hi == lo) continue;
+            threads.emplace_back([&, k, lo, hi] {
+                std::vector<const uint8_t*> ptrs;
+                for (const auto& f : p.fields) ptrs.push_back(f.data() + 32 * lo);
+                afx_presentation_batch b{(uint16_t)p.kinds.size(), p.kinds.data(), hi - lo, ptrs.data(), ptrs.size()};
+                rc[k] = afx_verify_presentations(issuers_[k].raw(), &b, v.data() + lo, nullptr);
+            });
+        }
+        for (auto& t : threads) t.join();
+        for (int r : rc) if (r != AFX_OK) throw Error(r);
+        return Issuer::to_results(v);
+    }
+
+private:
+    std::vector<Issuer> issuers_;
 };
 
 // CredentialIssuance::verify (src/issuer.rs:48-57), batch form; needs only the public parameters held by `params`.

@@ -83,6 +83,14 @@ int main(int argc, char** argv) {
         CHECK(vw[i].is_ok() == v[i].is_ok());
         if (v[i].is_err()) { CHECK(v[i].error == CredentialError::VerificationFailure); rejected++; }
     }
+    // one process, two contexts, two host threads (the single-process form of the multi-GPU sharding)
+    {
+        MultiGpuIssuer multi(std::vector<uint8_t>(issuer_bytes.begin(), issuer_bytes.begin() + a), std::vector<uint8_t>(issuer_bytes.begin() + a, issuer_bytes.begin() + a + 64),
+                             std::vector<uint8_t>(issuer_bytes.begin() + a + 64, issuer_bytes.end()), {0, 0}, max_batch);
+        auto vm = multi.verify_batch(cb);
+        CHECK(vm.size() == count && multi.devices() == 2);
+        for (uint32_t i = 0; i < count; i++) CHECK(vm[i].is_ok() == v[i].is_ok());
+    }
     try { user.verify_batch(cb); CHECK(!"a context without the issuer key must not verify presentations"); } catch (const Error& e) { CHECK(e.code == AFX_ERR_NO_SECRET); }
     std::printf("host_parity ok: %u items, %zu rejected, %s\n", count, rejected, afx_version());
     return 0;

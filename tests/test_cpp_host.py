@@ -37,7 +37,7 @@ def write_fixture(path, coracle, count):
 
 
 def build_driver(out, lib_dir, lib_name):
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", out, SRC, "-L" + lib_dir, "-l" + lib_name, "-Wl,-rpath," + lib_dir])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-o", out, SRC, "-L" + lib_dir, "-l" + lib_name, "-Wl,-rpath," + lib_dir])
 
 
 def test_cpp_host_mirror_on_emulation(tmp_path, coracle):

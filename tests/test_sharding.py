@@ -54,3 +54,42 @@ def test_sharded_verify_gloo(tmp_path, coracle, world):
     res = json.load(open(out))
     assert res == {"world": world, "presentations_ok": True, "rejected": [3, 22, 44], "issuances_ok": True, "mixed_ok": True,
                    "mixed_rejected": 4}
+
+
+def run_multi_gpu_issuer(coracle, binding, devices, count, max_batch):
+    from aeonflux_b200 import PresentationBatch
+    from aeonflux_b200.shard import MultiGpuIssuer
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"multi", 0, count)
+    for i, w, b in ((1, 1, 0), (count // 2, 9, 5), (count - 1, 20, 31)):
+        pres[i, w, b] ^= 1
+    issu[count // 3, 6, 2] ^= 4
+    ov, _ = orc.verify_presentations(kinds, pres)
+    oi, _ = orc.verify_issuances(bytes([0, 0, 2, 2]), issu)
+    m = MultiGpuIssuer(sp, ip, sk, devices=devices, max_batch=max_batch, _binding=binding)
+    try:
+        for _ in range(3):      # repeated: the per-context threads are reused
+            assert (m.verify_batch(PresentationBatch.from_items(kinds, pres, host_array=m.host_array)) == ov).all()
+        assert (m.verify_issuance_batch(PresentationBatch.from_items(bytes([0, 0, 2, 2]), issu)) == oi).all()
+        assert ov.sum() == 3 and oi.sum() == 1
+        assert len(m.verify_batch(PresentationBatch.from_items(kinds, pres[:0]))) == 0
+        assert (m.verify_batch(PresentationBatch.from_items(kinds, pres[:2])) == ov[:2]).all()      # fewer items than devices
+    finally:
+        m.close()
+
+
+def test_multi_gpu_issuer_threads_on_emulation(coracle):
+    """One process, three contexts, three host threads (the single-process form of the sharding) on the host emulation."""
+    import ctypes
+    from aeonflux_b200._binding import Binding
+    from tests.test_host_logic import build_hostemu
+    run_multi_gpu_issuer(coracle, Binding(ctypes.CDLL(build_hostemu())), devices=[0, 0, 0], count=23, max_batch=4)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_issuer_threads_on_gpu(coracle):
+    """The same on the CUDA library: one context per visible GPU plus a second context on GPU 0, each driven by its own thread."""
+    import torch
+    devices = list(range(torch.cuda.device_count())) + [0]
+    run_multi_gpu_issuer(coracle, None, devices=devices, count=5000, max_batch=1024)
