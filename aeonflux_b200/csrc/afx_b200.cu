@@ -6,6 +6,7 @@
 // access is a 128-bit load/store of an item-contiguous record.  Work is integer-multiply bound (IMAD.WIDE on the fma
 // pipe); there is no GEMM-shaped step, so no tensor cores, and HBM traffic is ~20 KB per presentation.
 #include <cuda_runtime.h>
+#include <atomic>
 
 #include <cstdio>
 
@@ -319,12 +320,12 @@ static void be_launch_points(const Workspace& ws, const PointJob* d_jobs, u32 nj
 }
 // The opt-in to > 48 KiB of dynamic shared memory is a per-device function attribute: set it once per (kernel, device).
 static void allow_large_smem(const void* kernel, int which) {
-    static bool done[2][64] = {};
+    static std::atomic<bool> done[2][64];          // contexts on different devices are driven from different host threads
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !done[which][dev]) {
+    if (dev < 0 || dev >= 64 || !done[which][dev].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (dev >= 0 && dev < 64) done[which][dev] = true;
+        if (dev >= 0 && dev < 64) done[which][dev].store(true, std::memory_order_release);
     }
 }
 
