@@ -23,7 +23,6 @@ constexpr int TPB = 128;            // threads per CTA for the ladder kernels (4
 // B200 (README-4, fused ladders): 1 x 512 threads/SM 24.4 ms, 2 x 256 23.6 ms (finer tail), 4 x 128 25.7 ms (I-cache misses return).
 constexpr int TPB_MSM = AFX_TPB_MSM;
 constexpr size_t LADDER_SMEM_BUDGET = (size_t)(200 / AFX_MSM_MINB) * 1024;   // per CTA, so that AFX_MSM_MINB CTAs fit one SM
-constexpr int MSM_STAGE_TABLES = 3; // constant-base tables staged in shared memory per CTA (12 KB each)
 
 __global__ void __launch_bounds__(256) k_scalar_check(Workspace ws, const u16* fields) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,13 +82,6 @@ __global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_ladders(Workspace ws,
     const u32 mi = a.group_idx[y];
     const MsmDesc& d = a.msms[mi];
     u32* scratch = smem;                                            // [scratch_terms*8][TPB_MSM]
-    u32* staged = smem + (size_t)a.scratch_terms * 8 * blockDim.x;  // [<=MSM_STAGE_TABLES][128][24]
-    u32 nstage = d.ncon < MSM_STAGE_TABLES ? d.ncon : MSM_STAGE_TABLES;
-    for (u32 k = 0; k < nstage; k++) {
-        const uint4* src = reinterpret_cast<const uint4*>(ws.ctabs + (size_t)d.con[k].ctab * CTAB_ENTRIES * 24);
-        uint4* dst = reinterpret_cast<uint4*>(staged + (size_t)k * CTAB_ENTRIES * 24);
-        for (u32 i = threadIdx.x; i < CTAB_ENTRIES * 24 / 4; i += blockDim.x) dst[i] = src[i];
-    }
     if ((int)mi == a.dep_msm && threadIdx.x == 0) {
         u32 lo = (bx * blockDim.x) / a.flag_tpb;
         u32 last_item = bx * blockDim.x + blockDim.x - 1;
@@ -98,7 +90,7 @@ __global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_ladders(Workspace ws,
             while (ld_acquire(a.flags + f) != a.epoch) __nanosleep(256);
     }
     __syncthreads();
-    CtabResolver ctab_of{staged, ws.ctabs, &d, nstage};
+    CtabResolver ctab_of{ws.ctabs, &d};
     msm_job(ws, d, item, scratch + threadIdx.x, blockDim.x, ctab_of, active);
 }
 
@@ -333,13 +325,13 @@ static void allow_large_smem(const void* kernel, int which) {
 // The last n_dep_jobs entries of d_idx are the MSMs that wait on the aMAC flags.
 static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac_nps, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 n_dep_jobs,
                              u32 max_terms, u32 max_con, int dep_msm, u32* flags, u32 epoch, u32 flag_tpb, be_stream s) {
-    u32 nstage = max_con < (u32)MSM_STAGE_TABLES ? max_con : (u32)MSM_STAGE_TABLES;
+    (void)max_con;
     u32 terms = max_terms > amac_nps ? max_terms : amac_nps;
-    // largest CTA (<= TPB_MSM threads) whose digit scratch + staged tables fit in shared memory
+    // largest CTA (<= TPB_MSM threads) whose digit scratch fits in shared memory
     u32 tpb = TPB_MSM;
     size_t smem = 0;
     for (;; tpb /= 2) {
-        smem = (size_t)terms * 8 * tpb * 4 + (size_t)nstage * CTAB_ENTRIES * 96;
+        smem = (size_t)terms * 8 * tpb * 4;
         if (smem <= LADDER_SMEM_BUDGET || tpb <= 32) break;
     }
     allow_large_smem((const void*)k_ladders, 0);

@@ -28,7 +28,7 @@ namespace afx {
 constexpr int MAX_ATTRS = 32;
 constexpr int MAX_VAR_TERMS = MAX_ATTRS + 4;
 constexpr int MAX_CONST_TERMS = MAX_ATTRS + 8;
-constexpr int CTAB_ENTRIES = 128;  // radix-256 signed digits: multiples 1..128 of a constant base
+constexpr int CTAB_ENTRIES = 2048; // radix-4096 signed digits: multiples 1..2048 of a constant base (192 KiB per generator, L2-resident)
 
 // ---- scalar sources ---------------------------------------------------------------------------
 enum : u32 { SC_FIELD = 0, SC_MUL = 1, SC_MULADD = 2 };  // R[f0] | R[f0]*R[f1] | R[f0] + R[f1]*R[f2]
@@ -386,17 +386,15 @@ AFX_HD void ztable_job(const Workspace& ws, const AmacDesc& d, u32 item) {
     store_table8(table_ptr(ws, d.out_table_slot, item), load_ge(ext_ptr(ws, d.out_ext_slot, item)));
 }
 
-// Where constant term k's radix-256 table lives: the first `nstage` are staged in shared memory by the CTA.
+// Where constant term k's radix-4096 table lives (global memory; 192 KiB per generator stay L2-resident).
 struct CtabResolver {
-    const u32* staged; const u32* global; const MsmDesc* d; u32 nstage;
-    AFX_HD const u32* operator()(u32 k) const {
-        return k < nstage ? staged + (size_t)k * CTAB_ENTRIES * 24 : global + (size_t)d->con[k].ctab * CTAB_ENTRIES * 24;
-    }
+    const u32* global; const MsmDesc* d;
+    AFX_HD const u32* operator()(u32 k) const { return global + (size_t)d->con[k].ctab * CTAB_ENTRIES * 24; }
 };
 
 // ---- stage: msm -----------------------------------------------------------------------------------------------
 // scratch: (nvar + ncon) * 8 words per item of recoded scalars.  ctab_of(k) returns the table base of constant term k
-// (shared-memory staged on the device, global otherwise).
+// (global memory).
 template <typename CtabOf>
 AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratch, u32 scratch_stride, CtabOf ctab_of, bool active = true) {
     if (d.flags & MSM_COMB) {      // constant bases only: radix-16 comb, public digits index it directly, no doublings
@@ -427,7 +425,7 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
     }
     for (u32 k = 0; k < d.ncon; k++) {
         u32 rec[8];
-        sc_recode256(rec, eval_scalar(ws, d.con[k].s, item));
+        sc_bias4096(rec, eval_scalar(ws, d.con[k].s, item));
         for (int w = 0; w < 8; w++) scratch[((d.nvar + k) * 8 + w) * scratch_stride] = rec[w];
     }
     gc cacc = gc_identity();
@@ -450,10 +448,9 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                 GE_LADDER_ADD(cacc, e);
             }
         }
-        if ((i & 1) == 0) {
+        if (i % 3 == 0) {      // a constant term contributes one radix-4096 digit every third window: 22 mixed additions per term
             for (u32 k = 0; k < d.ncon; k++) {
-                u32 word = scratch[((d.nvar + k) * 8 + (i >> 3)) * scratch_stride];
-                int dig = ((int)(word << (24 - 8 * ((i >> 1) & 3)))) >> 24;
+                int dig = sc_digit4096(scratch + (d.nvar + k) * 8 * scratch_stride, scratch_stride, i / 3);
                 if (dig != 0) {
                     u32 neg = ((u32)dig >> 31) ^ d.con[k].neg;
                     u32 mag = (u32)(dig < 0 ? -dig : dig);
@@ -820,12 +817,12 @@ AFX_HD void transcript_job(const Workspace& ws, const TxDesc& d, u32 item) {
 }
 
 // ---- setup (per issuer): constant tables --------------------------------------------------------------------------
-// entry (base b, multiple m in 1..128) of the radix-256 table: m*P in affine Niels form.
+// entry (base b, multiple m in 1..2048) of the radix-4096 table: m*P in affine Niels form.
 AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words*/) {
     ge p; u32 ok = ge_decompress(p, enc);
     ge acc = ge_identity();
     pniels pn = ge_to_pniels(p);
-    for (int bit = 7; bit >= 0; bit--) {
+    for (int bit = 11; bit >= 0; bit--) {
         acc = ge_dbl(acc, true);
         if ((m >> bit) & 1u) acc = ge_add_pn(acc, pn, true);
     }

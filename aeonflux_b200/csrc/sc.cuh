@@ -124,5 +124,21 @@ AFX_HD void sc_recode256(u32* out, const sc& a) {
 AFX_HD int sc_digit256(const u32* rec, int i) {
     return ((int)(rec[i >> 2] << (24 - 8 * (i & 3)))) >> 24;
 }
+// Signed radix-4096 digits without a carry pass: out = a + B with B = sum_{j<21} 2048 * 4096^j, so that digit j < 21 is
+// (bits [12j, 12j+12) of out) - 2048 in [-2048, 2047] and digit 21 is the unbiased top, out >> 252 in {0..3}:
+// sum_j digit_j * 4096^j = out - B = a.  A canonical scalar is < 2^253 and B < 2^252, so out fits the 8 words.
+AFX_HD void sc_bias4096(u32* out, const sc& a) {
+    const u32 B[8] = {0x00800800u, 0x08008008u, 0x80080080u, 0x00800800u, 0x08008008u, 0x80080080u, 0x00800800u, 0x08008008u};
+    u64 c = 0;
+    for (int w = 0; w < 8; w++) { c += (u64)a.v[w] + B[w]; out[w] = (u32)c; c >>= 32; }
+}
+// digit j (0..21) of a biased scalar whose word w is at rec[w * stride]
+AFX_HD int sc_digit4096(const u32* rec, u32 stride, int j) {
+    if (j >= 21) return (int)(rec[7 * stride] >> 28);
+    const u32 bit = 12u * (u32)j, w = bit >> 5, sh = bit & 31u;
+    u32 v = rec[w * stride] >> sh;
+    if (sh > 20u) v |= rec[(w + 1) * stride] << (32u - sh);
+    return (int)(v & 0xfffu) - 2048;
+}
 
 }  // namespace afx
