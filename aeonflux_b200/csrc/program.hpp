@@ -178,10 +178,12 @@ struct MsmBuilder {
     }
 };
 
-// A job with constant bases only runs on the comb tables when 64 mixed adds per term beat 252 shared doublings + 32 per term
-// (fewer than 7 terms).
+// A job with constant bases only runs on the comb tables (64 mixed adds per term, no doublings) when that beats the ladder:
+// verify paths, public digits: 252 shared doublings + 22 radix-4096 adds per term, i.e. fewer than 5 terms;
+// prover paths, secret digits: the ladder also needs 64 scanned adds per term, i.e. up to the scratch limit (fewer than 7 terms).
 inline void mark_comb_jobs(ShapeProgram& P) {
-    for (MsmDesc& d : P.msms) if (d.nvar == 0 && d.ncon > 0 && d.ncon < 7 && !(d.flags & MSM_ADD_W)) d.flags |= MSM_COMB;
+    const u32 limit = P.is_issue ? 7 : 5;
+    for (MsmDesc& d : P.msms) if (d.nvar == 0 && d.ncon > 0 && d.ncon < limit && !(d.flags & MSM_ADD_W)) d.flags |= MSM_COMB;
 }
 
 // Fold the hole-free leading blocks into a midstate, append the rest to the program.
