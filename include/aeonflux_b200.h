@@ -218,7 +218,9 @@ int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t
  *   op 5..8: in [count][2][32] raw 256-bit limb vectors a, b (any value in [0, 2^256) is a legal lazily reduced field element)
  *                                               -> canonical bytes of a*b, a^2, a+b, a-b mod 2^255-19
  *   op 9: same inputs                           -> canonical ((a+b)(a-b))^2 (a-b) + a     (chained unreduced intermediates)
- *   op 10: in [count][2][32] scalar, encoding   -> compress(scalar * point) through the completed-coordinates ladder forms */
+ *   op 10: in [count][2][32] scalar, encoding   -> compress(scalar * point) through the completed-coordinates ladder forms
+ *   op 11: in [count][32] a 256-bit integer     -> the integer recomposed from its biased radix-4096 digits (the recoding of the
+ *                                                  constant-base terms); ok = every digit within [-2048, 2048] */
 int afx_selftest_primitive(afx_ctx* ctx, int op, const uint8_t* in, size_t count, uint8_t* out, uint8_t* ok);
 
 /* Number of kernels this library launched on behalf of `ctx` so far (bench.py's gpu_launches). */

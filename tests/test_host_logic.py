@@ -302,6 +302,16 @@ def check_primitives(iss, coracle):
     got, ok = iss.selftest_primitive("scalarmult", np.concatenate([scal, pts], axis=1))
     assert ok3.all() and (got3 == got).all()
     check_field_edges(iss)
+    # biased radix-4096 recoding of the constant-base scalars: the digits recompose to the scalar, for edge patterns of 12-bit fields
+    # (0x000 -> digit -2048, 0x800 -> 0, 0xfff -> 2047), the group order's neighbours and random canonical scalars
+    ell = 2**252 + 27742317777372353535851937790883648493
+    pat = lambda f: sum(f << (12 * j) for j in range(21))
+    cases = [0, 1, ell - 1, ell, 2**252, 2**253 - 1, pat(0x800), pat(0x7ff), pat(0xfff), pat(0x000) + (1 << 252), pat(0x801), 2**256 - 2**252 - 1]
+    cases += [int.from_bytes(rng.bytes(32), "little") % ell for _ in range(500)]
+    cases += [sum(int(rng.choice([0, 0x7ff, 0x800, 0x801, 0xfff, 1])) << (12 * j) for j in range(21)) for _ in range(200)]
+    rec_in = np.frombuffer(b"".join(c.to_bytes(32, "little") for c in cases), np.uint8).reshape(-1, 32)
+    rec_out, rec_ok = iss.selftest_primitive("recode4096", rec_in)
+    assert rec_ok.all() and (rec_out == rec_in).all()
 
 
 def check_field_edges(iss, n_random=3000):
