@@ -235,11 +235,11 @@ __global__ void __launch_bounds__(256) k_verdict(Workspace ws, uint8_t* verdicts
 }
 
 // per-issuer setup: one thread per (constant point, multiple)
-__global__ void __launch_bounds__(128) k_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encneg, u32* bad) {
+__global__ void __launch_bounds__(128) k_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encneg, u32* bad, u32 entries, int bits) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ncp * CTAB_ENTRIES) return;
-    u32 b = t / CTAB_ENTRIES, m = t % CTAB_ENTRIES + 1;
-    u32 ok = ctab_entry_job(enc + 8 * b, m, ctabs + ((size_t)b * CTAB_ENTRIES + (m - 1)) * 24);
+    if (t >= ncp * entries) return;
+    u32 b = t / entries, m = t % entries + 1;
+    u32 ok = ctab_entry_job(enc + 8 * b, m, ctabs + ((size_t)b * entries + (m - 1)) * 24, bits + 1);
     if (m == 1) {
         ge p; u32 w[8];
         ge_decompress(p, enc + 8 * b);
@@ -383,10 +383,13 @@ static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d_desc, u32 ncterms
 static void be_launch_verdict(const Workspace& ws, uint8_t* verdicts, be_stream s) {
     k_verdict<<<grid_for(ws.count, 256, 1), 256, 0, s>>>(ws, verdicts);
 }
-static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d_encneg, u32* d_bad, be_stream s) {
-    u32 total = ncp * CTAB_ENTRIES;
-    k_ctab_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_ctabs, d_encneg, d_bad);
+// entries = 2^bits multiples 1..2^bits of every constant point
+static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d_encneg, u32* d_bad, int bits, be_stream s) {
+    u32 entries = 1u << bits, total = ncp * entries;
+    k_ctab_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_ctabs, d_encneg, d_bad, entries, bits);
 }
+// how many bytes of radix-2^16 constant tables an issuer may have (they must stay L2-resident next to the ladders' streaming traffic)
+static size_t be_ctab16_budget() { return (size_t)72 << 20; }
 static void be_launch_comb_setup(const u32* d_enc, u32 ncp, u32* d_comb, be_stream s) {
     u32 total = ncp * COMB_WINDOWS * COMB_ENTRIES;
     k_comb_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_comb);

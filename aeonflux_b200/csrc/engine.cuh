@@ -29,6 +29,7 @@ constexpr int MAX_ATTRS = 32;
 constexpr int MAX_VAR_TERMS = MAX_ATTRS + 4;
 constexpr int MAX_CONST_TERMS = MAX_ATTRS + 8;
 constexpr int CTAB_ENTRIES = 2048; // radix-4096 signed digits: multiples 1..2048 of a constant base (192 KiB per generator, L2-resident)
+constexpr int CTAB16_ENTRIES = 32768;  // optional radix-2^16 tables (3 MB per generator), built when all of an issuer's fit the L2 budget
 
 // ---- scalar sources ---------------------------------------------------------------------------
 enum : u32 { SC_FIELD = 0, SC_MUL = 1, SC_MULADD = 2 };  // R[f0] | R[f0]*R[f1] | R[f0] + R[f1]*R[f2]
@@ -111,7 +112,8 @@ struct Workspace {
     u32* status;         // [count]   0 = ok so far
     u32* derived;        // [n_derived][count][8]  per-item derived scalars (Issuer::issue only)
     // per-issuer constants
-    const u32* ctabs;    // [n_ctab][128][24]  affine Niels multiples 1..128
+    const u32* ctabs;    // [n_ctab][2048][24]   affine Niels multiples 1..2048
+    const u32* ctabs16;  // [n_ctab][32768][24]  multiples 1..32768, or null (the verify-path MSMs then use radix 4096)
     const u32* comb;     // [n_ctab][64][8][24]  radix-16 comb: (e * 16^i) * G
     const u32* secdig;   // [n_secret][8]      radix-16 recoded secret scalars (packed nibbles)
     const u32* secsc;    // [n_secret][8]      the same scalars, canonical words
@@ -418,6 +420,7 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
         if (active) store8(commit_ptr(ws, d.out_slot, item), w);
         return;
     }
+    const bool wide = ws.ctabs16 != nullptr;      // radix-2^16 constant tables: a digit every 4th window instead of every 3rd
     for (u32 k = 0; k < d.nvar; k++) {
         u32 rec[8];
         sc_recode16(rec, eval_scalar(ws, d.var[k].s, item));
@@ -425,7 +428,7 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
     }
     for (u32 k = 0; k < d.ncon; k++) {
         u32 rec[8];
-        sc_bias4096(rec, eval_scalar(ws, d.con[k].s, item));
+        if (wide) sc_bias65536(rec, eval_scalar(ws, d.con[k].s, item)); else sc_bias4096(rec, eval_scalar(ws, d.con[k].s, item));
         for (int w = 0; w < 8; w++) scratch[((d.nvar + k) * 8 + w) * scratch_stride] = rec[w];
     }
     gc cacc = gc_identity();
@@ -448,13 +451,16 @@ AFX_HD void msm_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scratc
                 GE_LADDER_ADD(cacc, e);
             }
         }
-        if (i % 3 == 0) {      // a constant term contributes one radix-4096 digit every third window: 22 mixed additions per term
+        // a constant term contributes one radix-4096 digit every third window (22 mixed additions per term), or one radix-2^16
+        // digit every fourth (16 per term) when the issuer's wide tables exist
+        if (wide ? (i & 3) == 0 : i % 3 == 0) {
             for (u32 k = 0; k < d.ncon; k++) {
-                int dig = sc_digit4096(scratch + (d.nvar + k) * 8 * scratch_stride, scratch_stride, i / 3);
+                const u32* rec = scratch + (d.nvar + k) * 8 * scratch_stride;
+                int dig = wide ? sc_digit65536(rec, scratch_stride, i >> 2) : sc_digit4096(rec, scratch_stride, i / 3);
                 if (dig != 0) {
                     u32 neg = ((u32)dig >> 31) ^ d.con[k].neg;
                     u32 mag = (u32)(dig < 0 ? -dig : dig);
-                    aniels e = load_aniels(ctab_of(k) + 24 * (mag - 1));
+                    aniels e = load_aniels((wide ? ws.ctabs16 + (size_t)d.con[k].ctab * CTAB16_ENTRIES * 24 : ctab_of(k)) + 24 * (size_t)(mag - 1));
                     e = aniels_cneg(e, neg);
                     GE_LADDER_MADD(cacc, e);
                 }
@@ -818,11 +824,11 @@ AFX_HD void transcript_job(const Workspace& ws, const TxDesc& d, u32 item) {
 
 // ---- setup (per issuer): constant tables --------------------------------------------------------------------------
 // entry (base b, multiple m in 1..2048) of the radix-4096 table: m*P in affine Niels form.
-AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words*/) {
+AFX_HD u32 ctab_entry_job(const u32* enc /*8 words*/, u32 m, u32* out /*24 words*/, int bits = 12) {
     ge p; u32 ok = ge_decompress(p, enc);
     ge acc = ge_identity();
     pniels pn = ge_to_pniels(p);
-    for (int bit = 11; bit >= 0; bit--) {
+    for (int bit = bits - 1; bit >= 0; bit--) {
         acc = ge_dbl(acc, true);
         if ((m >> bit) & 1u) acc = ge_add_pn(acc, pn, true);
     }

@@ -140,5 +140,15 @@ AFX_HD int sc_digit4096(const u32* rec, u32 stride, int j) {
     if (sh > 20u) v |= rec[(w + 1) * stride] << (32u - sh);
     return (int)(v & 0xfffu) - 2048;
 }
+// The same with 16-bit digits (radix 2^16, for issuers whose 3 MB-per-generator tables fit the L2): out = a + sum_{j<15} 32768 *
+// 65536^j; digit j < 15 is halfword j of out minus 32768, digit 15 is the unbiased top halfword (<= 2^13 + 1 for a canonical scalar).
+AFX_HD void sc_bias65536(u32* out, const sc& a) {
+    u64 c = 0;
+    for (int w = 0; w < 8; w++) { c += (u64)a.v[w] + (w < 7 ? 0x80008000u : 0x00008000u); out[w] = (u32)c; c >>= 32; }
+}
+AFX_HD int sc_digit65536(const u32* rec, u32 stride, int j) {
+    u32 h = (rec[(u32)(j >> 1) * stride] >> (16 * (j & 1))) & 0xffffu;
+    return j >= 15 ? (int)h : (int)h - 32768;
+}
 
 }  // namespace afx

@@ -86,26 +86,29 @@ static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d, u32 ncterms, con
     return 8;
 }
 static void be_launch_verdict(const Workspace& ws, uint8_t* v, be_stream) { for (u32 i = 0; i < ws.count; i++) v[i] = ws.status[i] != 0; }
-static void be_launch_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encneg, u32* bad, be_stream) {
+// wide (radix-2^16) tables only on request: building them on one core costs seconds per issuer
+static size_t be_ctab16_budget() { const char* e = std::getenv("AFX_HOSTEMU_CTAB16"); return e && e[0] == '1' ? (size_t)72 << 20 : 0; }
+static void be_launch_ctab_setup(const u32* enc, u32 ncp, u32* ctabs, u32* encneg, u32* bad, int bits, be_stream) {
+    const int CTAB_N = 1 << bits;
     // same entries as ctab_entry_job (m * P in affine Niels form, m = 1..CTAB_ENTRIES), walked as running sums with one shared
     // inversion per base (Montgomery's trick) instead of a ladder and an inversion per entry: the emulation runs on one core
-    std::vector<ge> mult(CTAB_ENTRIES);
-    std::vector<fe> pref(CTAB_ENTRIES);
+    std::vector<ge> mult(CTAB_N);
+    std::vector<fe> pref(CTAB_N);
     for (u32 b = 0; b < ncp; b++) {
         ge p; u32 ok = ge_decompress(p, enc + 8 * b);
         if (!ok) *bad |= 1;
         pniels pn = ge_to_pniels(p);
         mult[0] = p;
-        for (int m = 1; m < CTAB_ENTRIES; m++) mult[m] = ge_add_pn(mult[m - 1], pn, true);
+        for (int m = 1; m < CTAB_N; m++) mult[m] = ge_add_pn(mult[m - 1], pn, true);
         pref[0] = mult[0].Z;
-        for (int m = 1; m < CTAB_ENTRIES; m++) pref[m] = fe_mul(pref[m - 1], mult[m].Z);
-        fe z = pref[CTAB_ENTRIES - 1];
+        for (int m = 1; m < CTAB_N; m++) pref[m] = fe_mul(pref[m - 1], mult[m].Z);
+        fe z = pref[CTAB_N - 1];
         fe inv = fe_mul(fe_sqn(fe_pow_p58(z), 3), fe_mul(fe_sq(z), z));     // z^(p-2)
-        for (int m = CTAB_ENTRIES - 1; m >= 0; m--) {
+        for (int m = CTAB_N - 1; m >= 0; m--) {
             fe zinv = m ? fe_mul(inv, pref[m - 1]) : inv;
             if (m) inv = fe_mul(inv, mult[m].Z);
             fe x = fe_mul(mult[m].X, zinv), y = fe_mul(mult[m].Y, zinv);
-            u32* out = ctabs + ((size_t)b * CTAB_ENTRIES + m) * 24;
+            u32* out = ctabs + ((size_t)b * CTAB_N + m) * 24;
             store_fe(out, fe_add(y, x)); store_fe(out + 8, fe_sub(y, x)); store_fe(out + 16, fe_mul(fe_mul(x, y), FE_D2()));
         }
         ge_compress(encneg + 8 * b, ge_neg(p));

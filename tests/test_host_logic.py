@@ -430,3 +430,27 @@ def test_host_alloc_buffers(emu, coracle):
     emu.L.afx_host_free(None)
     z = iss.host_array((0, 32))
     assert z.shape == (0, 32)
+
+
+def test_wide_constant_tables_on_emulation(emu, coracle, monkeypatch):
+    """The radix-2^16 constant tables (built on the GPU for issuers with few generators; on the emulation only on request, they
+    take seconds on one core): Issuer::verify and CredentialIssuance::verify give the oracle's Z, commitments, challenges and
+    verdicts with them, as they do with the radix-4096 tables."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from tests.common import compare_with_oracle_trace
+    monkeypatch.setenv("AFX_HOSTEMU_CTAB16", "1")
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"wide-tables", 0, 9)
+    pres[4, 2, 1] ^= 2; pres[7, 20, 30] ^= 0x40
+    issu[3, 7, 0] ^= 1
+    iss = Issuer(sp, ip, sk, max_batch=5, _binding=emu)
+    monkeypatch.delenv("AFX_HOSTEMU_CTAB16")
+    assert iss.launch_count == Issuer(sp, ip, sk, max_batch=5, _binding=emu).launch_count + 1      # the extra table-setup pass ran
+    v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    compare_with_oracle_trace(v, dbg, ov, tr)
+    assert list(ov) == [0, 0, 0, 0, 1, 0, 0, 1, 0]
+    ik = bytes([0, 0, 2, 2])
+    oi, _ = orc.verify_issuances(ik, issu)
+    assert (iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu)) == oi).all() and oi.sum() == 1
