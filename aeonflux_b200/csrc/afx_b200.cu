@@ -388,8 +388,11 @@ static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d
     u32 entries = 1u << bits, total = ncp * entries;
     k_ctab_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_ctabs, d_encneg, d_bad, entries, bits);
 }
-// how many bytes of radix-2^16 constant tables an issuer may have (they must stay L2-resident next to the ladders' streaming traffic)
-static size_t be_ctab16_budget() { return (size_t)72 << 20; }
+// how many bytes of radix-2^16 constant tables an issuer may have
+#ifndef AFX_CTAB16_BUDGET_MB
+#define AFX_CTAB16_BUDGET_MB 200
+#endif
+static size_t be_ctab16_budget() { return (size_t)AFX_CTAB16_BUDGET_MB << 20; }
 static void be_launch_comb_setup(const u32* d_enc, u32 ncp, u32* d_comb, be_stream s) {
     u32 total = ncp * COMB_WINDOWS * COMB_ENTRIES;
     k_comb_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_comb);
