@@ -388,7 +388,8 @@ static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d
     u32 entries = 1u << bits, total = ncp * entries;
     k_ctab_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_ctabs, d_encneg, d_bad, entries, bits);
 }
-// how many bytes of radix-2^16 constant tables an issuer may have
+// How many bytes of radix-2^16 constant tables an issuer may have.  README-4's 20 generators (63 MB) sit in the 126 MB L2; S16's 44
+// (135 MB) do not fit entirely, but the gathers are skewed towards a few generators and the wide tables still win (570 -> 581 k/s).
 #ifndef AFX_CTAB16_BUDGET_MB
 #define AFX_CTAB16_BUDGET_MB 200
 #endif
