@@ -9,6 +9,7 @@
 #include <atomic>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "engine.cuh"
 
@@ -393,7 +394,12 @@ static void be_launch_ctab_setup(const u32* d_enc, u32 ncp, u32* d_ctabs, u32* d
 #ifndef AFX_CTAB16_BUDGET_MB
 #define AFX_CTAB16_BUDGET_MB 200
 #endif
-static size_t be_ctab16_budget() { return (size_t)AFX_CTAB16_BUDGET_MB << 20; }
+// AFX_CTAB16_BUDGET_MB in the environment overrides the built-in budget (0 = radix-4096 tables only).
+static size_t be_ctab16_budget() {
+    const char* e = std::getenv("AFX_CTAB16_BUDGET_MB");
+    if (e && *e) return (size_t)std::strtoull(e, nullptr, 10) << 20;
+    return (size_t)AFX_CTAB16_BUDGET_MB << 20;
+}
 static void be_launch_comb_setup(const u32* d_enc, u32 ncp, u32* d_comb, be_stream s) {
     u32 total = ncp * COMB_WINDOWS * COMB_ENTRIES;
     k_comb_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_comb);

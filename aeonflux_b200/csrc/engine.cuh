@@ -220,9 +220,17 @@ AFX_HD const u32* scalar_ref_ptr(const Workspace& ws, u32 ref, u32 item) {
     return field_ptr(ws, ref, item);
 }
 AFX_HD sc load_sc(const u32* p) { u32 w[8]; load8(w, p); return sc_from_words(w); }
+// A scalar that feeds a ladder.  Wire words are attacker-chosen 256-bit strings: one that is not canonical already has its
+// ST_BAD_SCALAR bit (k_scalar_check) and the item is rejected whatever the ladders compute, but the recodings below assume
+// a < l (sc_digit65536's top digit is the unbiased top halfword, sc_digit4096's the top nibble) and a table index must never
+// follow a wire value out of bounds -- so a non-canonical word enters every ladder as 0.  Products (SC_MUL / SC_MULADD) leave
+// sc_reduce512 canonical; secret rows are validated at afx_ctx_create; derived scalars and challenges are reduced on the device.
 AFX_HD sc eval_scalar(const Workspace& ws, const ScalarSrc& s, u32 item) {
     sc a = load_sc(scalar_ref_ptr(ws, s.f0, item));
-    if (s.op == SC_FIELD) return a;
+    if (s.op == SC_FIELD) {
+        if (s.f0 < SREF_SECRET) { u32 m = 0u - sc_is_canonical(a); for (int i = 0; i < 8; i++) a.v[i] &= m; }
+        return a;
+    }
     sc b = load_sc(scalar_ref_ptr(ws, s.f1, item));
     if (s.op == SC_MUL) return sc_mul(a, b);
     sc c = load_sc(scalar_ref_ptr(ws, s.f2, item));

@@ -109,3 +109,48 @@ def to_batchable(kinds, pres, commitments):
     for k, (src, idx) in enumerate(order):
         out[:, k] = pres[:, idx] if src == "w" else commitments[:, idx]
     return out
+
+
+def presentation_scalar_words(kinds):
+    """Indices of the words of the flat presentation layout (include/aeonflux_b200.h) that hold scalars."""
+    kinds = list(kinds)
+    n = len(kinds)
+    h_s = sum(k == 1 for k in kinds)
+    idx = list(range(0, 4 + h_s))                                  # challenge, responses[3 + h_s]
+    pos = 7 + h_s + n
+    for k in kinds:
+        if k in (0, 2):
+            if k == 0:
+                idx.append(pos)                                    # a revealed scalar
+            pos += 1
+    for k in kinds:
+        if k == 3:
+            idx += list(range(pos, pos + 7))                       # enc_challenge, enc_responses[6]
+            pos += 14
+    return idx
+
+
+def issuance_scalar_words(kinds):
+    n = len(kinds)
+    return [i for i, k in enumerate(kinds) if k == 0] + [n] + list(range(n + 3, 2 * n + 9))   # scalar attributes, t, challenge, responses
+
+
+NONCANONICAL_TOP_WORDS = (0x10000001, 0x1fffffff, 0x20010000, 0x2001ffff, 0x3fff8000, 0x40000000, 0x7fff0000, 0x7fffffff, 0x80000000,
+                          0x8000ffff, 0xc0007fff, 0xfffe8000, 0xffff0000, 0xffff7fff, 0xffff8000, 0xffffffff)
+
+
+def noncanonical_scalar_batch(items, scalar_words, rng):
+    """One copy of an honest item per (scalar word, top-word pattern): that word's top 32 bits are replaced by a pattern that
+    makes the 256-bit value >= l (the unbiased top digit of the radix-2^16 / radix-4096 recodings would index far past a
+    constant table), the low 224 bits are kept, zeroed or saturated.  Returns items [len(scalar_words) * 16][W][32]."""
+    out = []
+    for w in scalar_words:
+        for j, top in enumerate(NONCANONICAL_TOP_WORDS):
+            it = items[int(rng.integers(len(items)))].copy()
+            if j % 3 == 1:
+                it[w, :28] = 0
+            elif j % 3 == 2:
+                it[w, :28] = 0xff
+            it[w, 28:] = np.frombuffer(int(top).to_bytes(4, "little"), np.uint8)
+            out.append(it)
+    return np.stack(out)

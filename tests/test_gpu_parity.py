@@ -128,25 +128,30 @@ def test_device_resident_entry_point(readme4):
 
 
 def test_full_size_batch_round_trip_properties(readme4):
-    """BASELINE config 2 size (65,536 x README-4) through size-independent properties: every honest presentation is
-    accepted, every item with a flipped bit is rejected, and nothing else changes (linearity of the corruption set)."""
+    """BASELINE config 2 size through size-independent properties: 65,536 DISTINCT README-4 presentations (issued and shown on
+    the device from random attributes, bench.synthesize_on_device) are all accepted, every item with one flipped bit -- any
+    word, any byte including byte 31 with bit 255 and the scalars' top bits -- is rejected, and nothing else changes
+    (linearity of the corruption set); a sample is verified by the oracle."""
+    import torch
     from aeonflux_b200 import Issuer, PresentationBatch
+    from bench import KINDS_README4, synthesize_on_device
     orc, _, (sp, ip, sk) = readme4
-    base_n = 2048
-    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"full", 0, base_n, want_issuances=False)
-    reps = 65536 // base_n
-    big = np.tile(pres, (reps, 1, 1))
+    kinds = KINDS_README4
+    iss = Issuer(sp, ip, sk, device=0, max_batch=65536)
+    dev = synthesize_on_device(torch, iss, 65536, 77, torch.cuda.current_stream())      # bench_data's issuer and keypair are make_issuer(4)'s
+    big = np.ascontiguousarray(dev.cpu().numpy().transpose(1, 0, 2))
+    assert len(np.unique(big[:, 4:7].reshape(65536, -1), axis=0)) == 65536          # distinct commitments per item
+    assert not iss.verify_wire(kinds, big).any()
     rng = np.random.default_rng(3)
     bad = rng.choice(65536, 655, replace=False)
-    for i in bad:
+    for j, i in enumerate(bad):
         w = rng.integers(0, 28)
-        big[i, w, rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
-    iss = Issuer(sp, ip, sk, device=0, max_batch=65536)
+        big[i, w, 31 if j % 4 == 0 else rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
     v = iss.verify_batch(PresentationBatch.from_items(kinds, big))
     expect = np.zeros(65536, np.uint8)
     expect[bad] = 1
     assert (v == expect).all()
-    sample = np.concatenate([bad[:64], rng.choice(65536, 64, replace=False)])
+    sample = np.concatenate([bad[:96], rng.choice(65536, 64, replace=False)])
     ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(big[sample]))
     assert (v[sample] == ov).all()
 
@@ -206,7 +211,7 @@ def test_issue_full_size_round_trip(readme4):
     rr = np.random.default_rng(25)
     for i in bad:
         w = 4 + rr.integers(0, 13)
-        res.fields[w, i, rr.integers(0, 31)] ^= 1 << rr.integers(0, 8)
+        res.fields[w, i, rr.integers(0, 32)] ^= 1 << rr.integers(0, 8)
     v = iss.verify_issuance_batch(res)
     expect = np.zeros(count, np.uint8)
     expect[bad] = 1
@@ -233,7 +238,7 @@ def test_mixed_stream_reduced_config5(coracle):
         kinds, pres = base[n]
         w = pres[rng.integers(0, len(pres))].copy()
         if rng.random() < 0.01:
-            w[rng.integers(0, w.shape[0]), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+            w[rng.integers(0, w.shape[0]), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
             expect[i] = 1
         kl.append(kinds); items.append(w)
     v = ShardedIssuer(iss[4]).verify_mixed(kl, items, issuers=iss)
@@ -254,7 +259,7 @@ def test_multi_chunk_host_call_is_pipelined_and_exact(readme4):
     rng = np.random.default_rng(31)
     bad = rng.choice(count, 97, replace=False)
     for i in bad:
-        pres[i, rng.integers(0, 28), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+        pres[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
     iss = Issuer(sp, ip, sk, device=0, max_batch=1024)
     v = iss.verify_batch(PresentationBatch.from_items(kinds, pres))
     ov, _ = orc.verify_presentations(kinds, pres)
@@ -358,7 +363,7 @@ def test_batchable_proofs_exact_and_rlc_on_gpu(readme4):
     rng = np.random.default_rng(51)
     bad = np.array([5, 8191, 8192, 19999])                      # chunks 0, 0, 1, 2
     for i in bad:
-        bp[i, rng.integers(0, bp.shape[1]), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+        bp[i, rng.integers(0, bp.shape[1]), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
     batch = PresentationBatch.from_items(kinds, bp)
     expect = np.zeros(count, np.uint8); expect[bad] = 1
     assert (iss.verify_batchable(batch) == expect).all()
@@ -382,7 +387,7 @@ def test_async_submit_wait_on_gpu(readme4):
     items = pres[rng.integers(0, 1024, n_pass * per)].copy()
     bad = rng.choice(n_pass * per, 40, replace=False)
     for i in bad:
-        items[i, rng.integers(0, 28), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+        items[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
     expect = np.zeros(n_pass * per, np.uint8); expect[bad] = 1
     iss = Issuer(sp, ip, sk, device=0, max_batch=per)
     # odd passes are staged in page-locked memory from the library's allocator (afx_host_alloc), even ones in numpy memory
@@ -395,3 +400,14 @@ def test_async_submit_wait_on_gpu(readme4):
     got += [p.wait() for p in pending]
     assert (np.concatenate(got) == expect).all()
     assert (iss.verify_batch(PresentationBatch.from_items(kinds, items)) == expect).all()     # and the synchronous path still works after it
+
+
+@pytest.mark.parametrize("budget_mb", ["200", "0"])
+def test_noncanonical_wire_scalars_never_index_out_of_bounds_on_gpu(coracle, monkeypatch, budget_mb):
+    """wire scalars >= l with top-word patterns 0x2001xxxx .. 0xffffffff in every scalar field, under the radix-2^16
+    constant tables (default) and the radix-4096 ones (AFX_CTAB16_BUDGET_MB=0): rejected, no illegal address (a fault would poison
+    the context and fail every later call), and the same context keeps verifying honest batches."""
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_noncanonical_wire_scalars
+    monkeypatch.setenv("AFX_CTAB16_BUDGET_MB", budget_mb)
+    check_noncanonical_wire_scalars(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=4096), coracle, count=16)

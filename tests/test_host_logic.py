@@ -454,3 +454,37 @@ def test_wide_constant_tables_on_emulation(emu, coracle, monkeypatch):
     ik = bytes([0, 0, 2, 2])
     oi, _ = orc.verify_issuances(ik, issu)
     assert (iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu)) == oi).all() and oi.sum() == 1
+
+
+def check_noncanonical_wire_scalars(make_issuer, coracle, count=3):
+    """Every scalar word of a presentation / issuance replaced by 256-bit values >= l whose top bits would, unmasked, drive the
+    unbiased top digit of the constant-table recodings far out of bounds (response z = 0xffff0000... read 3 MB past the
+    radix-2^16 table of I).  The items are rejected like the oracle rejects them, nothing faults, and the context keeps verifying."""
+    from aeonflux_b200 import PresentationBatch
+    from tests.common import issuance_scalar_words, noncanonical_scalar_batch, presentation_scalar_words
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"noncanonical", 0, count)
+    iss = make_issuer(sp, ip, sk)
+    rng = np.random.default_rng(5)
+    bad = noncanonical_scalar_batch(pres, presentation_scalar_words(kinds), rng)
+    assert len(bad) == 13 * 16
+    ov, _ = orc.verify_presentations(kinds, bad)
+    assert ov.all()
+    assert (iss.verify_batch(PresentationBatch.from_items(kinds, bad)) == 1).all()
+    assert (iss.verify_wire(kinds, bad) == 1).all()
+    ik = bytes([0, 0, 2, 2])
+    ibad = noncanonical_scalar_batch(issu, issuance_scalar_words(ik), rng)
+    oi, _ = orc.verify_issuances(ik, ibad)
+    assert oi.all()
+    assert (iss.verify_issuance_batch(PresentationBatch.from_items(ik, ibad)) == 1).all()
+    assert not iss.verify_batch(PresentationBatch.from_items(kinds, pres)).any()
+    assert not iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu)).any()
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_noncanonical_wire_scalars_never_index_out_of_bounds(emu, coracle, monkeypatch, wide):
+    from aeonflux_b200 import Issuer
+    if wide:
+        monkeypatch.setenv("AFX_HOSTEMU_CTAB16", "1")
+    check_noncanonical_wire_scalars(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=64, _binding=emu), coracle)

@@ -34,7 +34,7 @@ def run_shapes(coracle, binding, seed, trials, count, device_kw):
             assert not iss.verify_batchable(PresentationBatch(kinds, bf)).any()
             vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes([trial] * 32))
             assert not vr.any() and fb == 0, (n, rk, hide)
-            bf[int(rng.integers(0, bf.shape[0])), count - 1, int(rng.integers(0, 31))] ^= 1 << int(rng.integers(0, 8))
+            bf[int(rng.integers(0, bf.shape[0])), count - 1, int(rng.integers(0, 32))] ^= 1 << int(rng.integers(0, 8))
             expect = np.zeros(count, np.uint8); expect[count - 1] = 1
             assert (iss.verify_batchable(PresentationBatch(kinds, bf)) == expect).all()
             vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes([trial] * 32))

@@ -26,7 +26,7 @@ for it in range(iters):
     items = base[rng.integers(0, len(base), count)].copy()
     bad = np.unique(rng.integers(0, count, max(1, count // 300)))
     for i in bad:
-        items[i, rng.integers(0, 28), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+        items[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
     expect = np.zeros(count, np.uint8); expect[bad] = 1
     mode = it % 3
     if mode == 0:
