@@ -35,12 +35,15 @@ __global__ void __launch_bounds__(TPB, 4) k_points(Workspace ws, const PointJob*
     if (item < ws.count) points_job(ws, jobs[blockIdx.y], item);
 }
 
-// All ladders of a verify pipeline in ONE launch: blockIdx.y = 0 is the aMAC ladder (when the shape has one), the rest are
-// the constraint MSMs.  The aMAC ladder is bound by its constant-address table scans (HBM), the MSMs by the IMAD pipe;
+// All ladders of a verify pipeline in ONE launch: the aMAC ladder (when the shape has one) and the constraint MSMs.
+// The aMAC ladder is bound by its constant-address table scans (HBM), the MSMs by the IMAD pipe;
 // sharing a grid lets the SMs that run aMAC CTAs stream their tables while the others multiply, instead of every SM
 // contending for HBM at once.  The one MSM that consumes Z (constraint "Z", presentation.rs:416) is ordered last and waits
-// on a per-CTA completion flag written by the aMAC CTAs (release/acquire at gpu scope; CTAs are dispatched in block-index
-// order, so the producers are always scheduled before any consumer).
+// on a per-CTA completion flag written by the aMAC CTAs (release/acquire at gpu scope).
+// Work is claimed through an atomic TICKET, not blockIdx: a CTA's position in the block order below is the value it draws from
+// a per-launch counter when it starts running.  Every position below a consumer's was therefore drawn by a CTA that is already
+// resident and running, so a spinning consumer can only ever wait for producers that are making progress -- whatever order
+// the hardware, MPS or a debugger dispatches CTAs in.
 __device__ __forceinline__ u32 ld_acquire(const u32* p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
@@ -48,6 +51,7 @@ struct LadderArgs {
     const MsmDesc* msms; const u32* group_idx; u32 scratch_terms;
     const AmacDesc* amac;     // nullable
     u32* flags; u32 epoch; u32 flag_tpb; int dep_msm;   // MSM index that must wait for the aMAC CTAs covering its items (-1 none)
+    u32* ticket;                    // zeroed on the stream before the launch
     u32 nx, n_ind, n_dep, stride;   // block order, see ladder_block()
 };
 // Block order of the fused launch (1-D grid).  nx = CTAs per job.  First the n_ind independent MSM jobs (job-major) with one
@@ -67,8 +71,11 @@ __device__ __forceinline__ int ladder_block(const LadderArgs& a, u32 b, u32& bx)
 
 __global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_ladders(Workspace ws, LadderArgs a) {
     extern __shared__ __align__(16) u32 smem[];
+    __shared__ u32 s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
     u32 bx;
-    const int job = ladder_block(a, blockIdx.x, bx);
+    const int job = ladder_block(a, s_ticket, bx);
     u32 item = bx * blockDim.x + threadIdx.x;
     bool active = item < ws.count;
     if (!active) item = ws.count - 1;                              // keep every thread in the barriers of the ladder
@@ -325,7 +332,7 @@ static void allow_large_smem(const void* kernel, int which) {
 // One launch for the aMAC ladder (if `amac`) plus the MSMs of one scratch-size group.
 // The last n_dep_jobs entries of d_idx are the MSMs that wait on the aMAC flags.
 static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac_nps, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 n_dep_jobs,
-                             u32 max_terms, u32 max_con, int dep_msm, u32* flags, u32 epoch, u32 flag_tpb, be_stream s) {
+                             u32 max_terms, u32 max_con, int dep_msm, u32* flags, u32 epoch, u32 flag_tpb, u32* ticket, be_stream s) {
     (void)max_con;
     u32 terms = max_terms > amac_nps ? max_terms : amac_nps;
     // largest CTA (<= TPB_MSM threads) whose digit scratch fits in shared memory
@@ -341,7 +348,8 @@ static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac
     const u32 head = n_ind * nx + (amac ? nx : 0);
     u32 stride = amac ? (u32)((uint64_t)head * 7 / 10 / nx) : 1;   // aMAC CTAs spread over the first 70% of the independent work
     if (stride < 1) stride = 1;
-    LadderArgs a{d_msms, d_idx, terms, amac, flags, epoch, amac ? tpb : flag_tpb, dep_msm, nx, n_ind, n_dep, stride};
+    LadderArgs a{d_msms, d_idx, terms, amac, flags, epoch, amac ? tpb : flag_tpb, dep_msm, ticket, nx, n_ind, n_dep, stride};
+    cudaMemsetAsync(ticket, 0, 4, s);
     k_ladders<<<nx * (nidx + (amac ? 1 : 0)), tpb, smem, s>>>(ws, a);
     return tpb;
 }

@@ -7,8 +7,9 @@
  * A batch entry point added beside each of those (Issuer::verify_batch, Issuer::issue_batch,
  * CredentialIssuance::verify_batch -- see INTEGRATION.md for the Rust shim) flattens its arguments to the plain
  * buffers below and binds exactly these symbols.  Plain pointers and sizes only; the caller owns every buffer; the
- * library copies what it keeps.  All functions are synchronous unless they take a stream.  A context is used by one thread at
- * a time (it owns one workspace and its CUDA streams); replicate it per GPU and per concurrent caller.
+ * library copies what it keeps.  All functions are synchronous unless they take a stream.  A context owns one workspace and
+ * its CUDA streams, so calls on ONE context serialise on an internal lock (safe from several threads, never concurrent);
+ * replicate the context per GPU and per concurrent caller -- or use the afx_multi_* entry points, which do that.
  *
  * Batch data is struct-of-arrays: "field f" is an array [count][32 bytes].  A 32-byte word is either a canonical
  * little-endian Scalar or a CompressedRistretto -- the same encodings the reference's to_bytes() methods emit
@@ -104,8 +105,10 @@ int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t*
 /* Asynchronous host calls for a caller that streams batches (SURVEY 8b "optional async/stream variant"): submit enqueues the
  * copy, the kernels and the verdict read-back of one pass (count <= max_batch) and returns a ticket; afx_wait(ticket) blocks until
  * the verdicts are in the array given at submission.  Up to two submissions may be outstanding per context, so the copy of one
- * overlaps the kernels of the other; a third submit, or any synchronous multi-pass call, while two are outstanding returns
- * AFX_ERR_ARG.  The field buffers and the verdict array must stay valid until afx_wait returns. */
+ * overlaps the kernels of the other; a third submit, or any synchronous call, while submissions are outstanding returns
+ * AFX_ERR_ARG.  The workspace is (re)sized only while nothing is in flight: a submit whose shape needs more of any workspace
+ * array than the outstanding submission was sized for also returns AFX_ERR_ARG -- wait, then submit (streams of one shape, or of
+ * shapes submitted largest first, never hit this).  The field buffers and the verdict array must stay valid until afx_wait returns. */
 int afx_verify_presentations_submit(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, uint64_t* ticket);
 int afx_verify_issuances_submit(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, uint64_t* ticket);
 int afx_wait(afx_ctx* ctx, uint64_t ticket);

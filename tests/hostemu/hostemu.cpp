@@ -41,7 +41,7 @@ static void be_launch_points(const Workspace& ws, const PointJob* jobs, u32 nj, 
     for (u32 k = 0; k < nj; k++) for (u32 i = 0; i < ws.count; i++) points_job(ws, jobs[k], i);
 }
 static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 nps, const MsmDesc* msms, const u32* idx, u32 nidx, u32, u32 max_terms, u32,
-                             int, u32*, u32, u32, be_stream) {
+                             int, u32*, u32, u32, u32*, be_stream) {
     std::vector<u32> scratch((size_t)(max_terms > nps ? max_terms : nps) * 8 + 8);
     if (amac) for (u32 i = 0; i < ws.count; i++) amac_job(ws, *amac, i, scratch.data(), 1);
     for (u32 k = 0; k < nidx; k++) {

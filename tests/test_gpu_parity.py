@@ -411,3 +411,31 @@ def test_noncanonical_wire_scalars_never_index_out_of_bounds_on_gpu(coracle, mon
     from tests.test_host_logic import check_noncanonical_wire_scalars
     monkeypatch.setenv("AFX_CTAB16_BUDGET_MB", budget_mb)
     check_noncanonical_wire_scalars(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=4096), coracle, count=16)
+
+
+def test_two_contexts_run_the_fused_ladders_concurrently(readme4):
+    """k_ladders claims its work by atomic ticket, so the consumer of Z only ever waits for producers that already run -- also when
+    a second context's grid competes for the same SMs.  Two contexts on device 0, driven from two threads, several passes each
+    with different corruption sets: every verdict vector is exact."""
+    from concurrent.futures import ThreadPoolExecutor
+    from aeonflux_b200 import Issuer, PresentationBatch
+    orc, _, (sp, ip, sk) = readme4
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"two-ctx", 0, 512, want_issuances=False)
+    per, passes = 16384, 6
+
+    def worker(seed):
+        rng = np.random.default_rng(seed)
+        iss = Issuer(sp, ip, sk, device=0, max_batch=per)
+        ok = True
+        for _ in range(passes):
+            items = pres[rng.integers(0, 512, per)].copy()
+            bad = rng.choice(per, 50, replace=False)
+            for i in bad:
+                items[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+            expect = np.zeros(per, np.uint8); expect[bad] = 1
+            ok &= bool((iss.verify_wire(kinds, items) == expect).all())
+        iss.close()
+        return ok
+
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        assert all(pool.map(worker, [101, 202]))

@@ -488,3 +488,23 @@ def test_noncanonical_wire_scalars_never_index_out_of_bounds(emu, coracle, monke
     if wide:
         monkeypatch.setenv("AFX_HOSTEMU_CTAB16", "1")
     check_noncanonical_wire_scalars(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=64, _binding=emu), coracle)
+
+
+def test_submit_refuses_a_shape_the_inflight_workspace_cannot_hold(emu, coracle):
+    """on a fresh context an issuance submit sizes the workspace for the issuance shape only (no aMAC tables,
+    no flags, n + 2 ladder tables).  A presentation submit right behind it must be refused while that one is in flight -- not run
+    the aMAC through unallocated arrays -- and succeed once the context is idle again."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    from aeonflux_b200._binding import AfxError
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPP", [], b"submit-ws", 0, 6)       # all revealed: 2n + 7 fields < the issuance's 2n + 9
+    ik = bytes([0, 0, 2, 2])
+    iss = Issuer(sp, ip, sk, max_batch=6, _binding=emu)
+    a = iss.submit(PresentationBatch.from_items(ik, issu), issuance=True)
+    with pytest.raises(AfxError):
+        iss.submit(PresentationBatch.from_items(kinds, pres))
+    assert not a.wait().any()
+    b = iss.submit(PresentationBatch.from_items(kinds, pres))            # idle: the workspace grows
+    c = iss.submit(PresentationBatch.from_items(ik, issu), issuance=True)  # fits what the presentation sized
+    assert not b.wait().any() and not c.wait().any()
