@@ -275,6 +275,22 @@ def check_primitives(iss, coracle):
     assert ok.all() and out.tobytes() == hx(g["scalarmult"], "out").tobytes()
     out, ok = iss.selftest_primitive("wide_reduce", hx(g["wide_reduce"], "in").reshape(-1, 64))
     assert out.tobytes() == hx(g["wide_reduce"], "out").tobytes()
+    # RFC 9496 Appendix A (tests/golden/rfc9496.json): generator multiples, every invalid encoding, hash-to-group
+    rfc = json.load(open(os.path.join(ROOT, "tests", "golden", "rfc9496.json")))
+    mult = np.frombuffer(bytes.fromhex("".join(rfc["multiples"])), np.uint8).reshape(16, 32)
+    ks = np.zeros((16, 32), np.uint8); ks[:, 0] = np.arange(16)
+    out, ok = iss.selftest_primitive("scalarmult", np.concatenate([ks, np.repeat(mult[1:2], 16, axis=0)], axis=1))
+    assert ok.all() and (out == mult).all()
+    out, ok = iss.selftest_primitive("ladder_scalarmult", np.concatenate([ks, np.repeat(mult[1:2], 16, axis=0)], axis=1))
+    assert ok.all() and (out == mult).all()
+    out, ok = iss.selftest_primitive("decompress_compress", mult)
+    assert ok.all() and (out == mult).all()
+    inv = np.frombuffer(bytes.fromhex("".join(h for grp in rfc["invalid"].values() for h in grp)), np.uint8).reshape(-1, 32)
+    out, ok = iss.selftest_primitive("decompress_compress", inv)
+    assert len(inv) == 29 and not ok.any()
+    h2g = np.frombuffer(bytes.fromhex("".join(e["input"] for e in rfc["hash_to_group"])), np.uint8).reshape(-1, 64)
+    out, ok = iss.selftest_primitive("from_uniform", h2g)
+    assert out.tobytes().hex() == "".join(e["output"] for e in rfc["hash_to_group"])
     # random inputs against the C oracle: edge scalars (0, 1, l-1) times a point, wide reductions of extreme values, a*b+c
     rng = np.random.default_rng(17)
     Lm1 = (2**252 + 27742317777372353535851937790883648493 - 1).to_bytes(32, "little")

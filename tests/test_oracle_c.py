@@ -44,6 +44,18 @@ def test_c_primitives(coracle):
     for e in g["wide_reduce"]:
         L.afxo_sc_from_wide(bytes.fromhex(e["in"]), out)
         assert bytes(out).hex() == e["out"]
+    rfc = json.load(open(os.path.join(GOLD, "rfc9496.json")))          # RFC 9496 Appendix A in full
+    B = bytes.fromhex(rfc["multiples"][1])
+    for k, h in enumerate(rfc["multiples"]):
+        for vt in (0, 1):
+            assert L.afxo_scalarmult(k.to_bytes(32, "little"), B, out, vt) == 1 and bytes(out).hex() == h
+        assert L.afxo_decompress_compress(bytes.fromhex(h), out) == 1 and bytes(out).hex() == h
+    for group, encs in rfc["invalid"].items():
+        for h in encs:
+            assert L.afxo_decompress_compress(bytes.fromhex(h), out) == 0, (group, h)
+    for e in rfc["hash_to_group"]:
+        L.afxo_from_uniform(bytes.fromhex(e["input"]), out)
+        assert bytes(out).hex() == e["output"]
     rng = A.ShakeRng(b"c-sc")
     for _ in range(200):
         a, b, c = rng.scalar(), rng.scalar(), rng.scalar()

@@ -54,6 +54,33 @@ def test_rfc9496_constants():
     assert (R.BASEPOINT * R.L).compress() == bytes(32)
 
 
+def test_rfc9496_appendix_a():
+    """RFC 9496 Appendix A in full (tests/golden/rfc9496.json): the 16 generator multiples (A.1), all 29 invalid encodings by
+    group (A.2), hash-to-group (A.3) -- Python oracle, and libsodium 1.0.20 beside it when loadable."""
+    g = json.load(open(os.path.join(GOLD, "rfc9496.json")))
+    lib = _sodium()
+    out = ctypes.create_string_buffer(32)
+    assert len(g["multiples"]) == 16
+    for k, h in enumerate(g["multiples"]):
+        assert (R.BASEPOINT * k).compress().hex() == h
+        dec = R.decompress(bytes.fromhex(h))
+        assert dec is not None and dec.compress().hex() == h
+        if lib is not None and k:
+            assert lib.crypto_scalarmult_ristretto255(out, k.to_bytes(32, "little"), R.BASEPOINT_COMPRESSED) == 0 and out.raw.hex() == h
+    assert sum(len(v) for v in g["invalid"].values()) == 29
+    for group, encs in g["invalid"].items():
+        for h in encs:
+            assert R.decompress(bytes.fromhex(h)) is None, (group, h)
+            if lib is not None:
+                assert not lib.crypto_core_ristretto255_is_valid_point(bytes.fromhex(h)), (group, h)
+    for e in g["hash_to_group"]:
+        assert hashlib.sha512(e["label"].encode()).hexdigest() == e["input"]
+        assert R.from_uniform_bytes(bytes.fromhex(e["input"])).compress().hex() == e["output"]
+        if lib is not None:
+            lib.crypto_core_ristretto255_from_hash(out, bytes.fromhex(e["input"]))
+            assert out.raw.hex() == e["output"]
+
+
 def test_transcript_regression_vector_v1():
     t = M.Transcript(b"2019/1416 anonymous credential")
     domain_sep(t, b"2019/1416 presentation proof")
