@@ -30,7 +30,11 @@ class AfxError(RuntimeError):
 class Binding:
     SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
                "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
-               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_host_alloc", "afx_host_free", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version"]
+               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_host_alloc", "afx_host_free", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_strerror", "afx_version",
+               "afx_multi_create", "afx_multi_destroy", "afx_multi_num_devices", "afx_multi_ctx", "afx_multi_verify_presentations",
+               "afx_multi_verify_presentations_wire", "afx_multi_verify_issuances", "afx_multi_verify_issuances_wire", "afx_multi_issue",
+               "afx_verify_presentations_wire_submit", "afx_verify_issuances_wire_submit", "afx_stream_create", "afx_stream_destroy",
+               "afx_stream_add_shape", "afx_stream_push", "afx_stream_flush", "afx_stream_buckets_submitted"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -93,6 +97,37 @@ class Binding:
         L.afx_strerror.restype = ctypes.c_char_p
         L.afx_strerror.argtypes = [ctypes.c_int]
         L.afx_version.restype = ctypes.c_char_p
+        for f in ("afx_verify_presentations_wire_submit", "afx_verify_issuances_wire_submit"):
+            getattr(L, f).restype = ctypes.c_int
+            getattr(L, f).argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, ctypes.POINTER(ctypes.c_uint64)]
+        L.afx_stream_create.restype = ctypes.c_int
+        L.afx_stream_create.argtypes = [ctypes.POINTER(vp)]
+        L.afx_stream_destroy.restype = None
+        L.afx_stream_destroy.argtypes = [vp]
+        L.afx_stream_add_shape.restype = ctypes.c_int
+        L.afx_stream_add_shape.argtypes = [vp, vp, ctypes.c_int, ctypes.c_uint16, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(sz)]
+        L.afx_stream_push.restype = ctypes.c_int
+        L.afx_stream_push.argtypes = [vp, vp, vp, vp, sz, vp]
+        L.afx_stream_flush.restype = ctypes.c_int
+        L.afx_stream_flush.argtypes = [vp]
+        L.afx_stream_buckets_submitted.restype = ctypes.c_uint64
+        L.afx_stream_buckets_submitted.argtypes = [vp]
+        L.afx_multi_create.restype = ctypes.c_int
+        L.afx_multi_create.argtypes = [vp, sz, vp, vp, sz, ctypes.POINTER(ctypes.c_int), ctypes.c_int, sz, ctypes.POINTER(vp)]
+        L.afx_multi_destroy.restype = None
+        L.afx_multi_destroy.argtypes = [vp]
+        L.afx_multi_num_devices.restype = ctypes.c_int
+        L.afx_multi_num_devices.argtypes = [vp]
+        L.afx_multi_ctx.restype = vp
+        L.afx_multi_ctx.argtypes = [vp, ctypes.c_int]
+        for f in ("afx_multi_verify_presentations", "afx_multi_verify_issuances"):
+            getattr(L, f).restype = ctypes.c_int
+            getattr(L, f).argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp]
+        for f in ("afx_multi_verify_presentations_wire", "afx_multi_verify_issuances_wire"):
+            getattr(L, f).restype = ctypes.c_int
+            getattr(L, f).argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp]
+        L.afx_multi_issue.restype = ctypes.c_int
+        L.afx_multi_issue.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), ctypes.POINTER(afx_issuance_out), vp]
 
     def check(self, rc):
         if rc != AFX_OK:

@@ -111,44 +111,167 @@ class ShardedIssuer:
 
 
 class MultiGpuIssuer:
-    """ONE process driving several B200s: a replicated `Issuer` context per device and one host thread per context (SURVEY 8e:
-    "one thread + stream set per GPU").  This is the form a single-process caller -- the reference is a library, its
-    `Issuer::verify_batch` shim runs inside the application -- uses instead of one process per GPU; the partition is the same
-    (contiguous item slices, no data-path communication, verdicts concatenated).  The C ABI is thread-compatible across contexts:
-    each context owns its streams, workspace and shape cache, and every call selects its device first; ctypes releases the GIL
-    for the duration of a call, so the device passes run concurrently."""
+    """ONE process driving several B200s through the C ABI's multi-device handle (afx_multi_*): the library
+    replicates the issuer context on every listed device, keeps one host thread + stream set per device, cuts every batch into
+    contiguous item slices [k*N/G, (k+1)*N/G) and lets each device write its slice of the verdict array.  This is the form a
+    single-process caller -- the reference is a library, its `Issuer::verify_batch` shim runs inside the application -- uses
+    instead of one process per GPU.  This class only marshals arguments."""
 
     def __init__(self, system_parameters, issuer_parameters, amacs_key=None, devices=(0,), max_batch=65536, _binding=None):
-        from concurrent.futures import ThreadPoolExecutor
-        from .issuer import Issuer
+        import ctypes
+        if _binding is None:
+            from ._lib import load
+            _binding = load()
         if not devices:
             raise ValueError("at least one device")
+        self._b = _binding
         self.devices = list(devices)
-        self.issuers = [Issuer(system_parameters, issuer_parameters, amacs_key, device=d, max_batch=max_batch, _binding=_binding) for d in self.devices]
-        self._pool = ThreadPoolExecutor(max_workers=len(self.devices))
+        self.max_batch = max_batch
+        sp, ip = bytes(system_parameters), bytes(issuer_parameters)
+        if len(ip) != 64:
+            raise ValueError("issuer_parameters must be C_W || I (64 bytes)")
+        self.number_of_attributes = int.from_bytes(sp[:4], "little")
+        sk = ctypes.create_string_buffer(bytes(amacs_key), len(amacs_key)) if amacs_key is not None else None
+        devs = (ctypes.c_int * len(self.devices))(*self.devices)
+        h = ctypes.c_void_p()
+        rc = self._b.L.afx_multi_create(sp, len(sp), ip, ctypes.addressof(sk) if sk is not None else None, len(amacs_key) if amacs_key is not None else 0,
+                                        devs, len(self.devices), max_batch, ctypes.byref(h))
+        if sk is not None:
+            ctypes.memset(sk, 0, len(amacs_key))
+        self._b.check(rc)
+        self._h = h
 
     def host_array(self, shape):
-        return self.issuers[0].host_array(shape)
+        return self._b.host_array(shape)
 
-    def _fan_out(self, method, batch):
-        g = len(self.issuers)
-        if batch.count == 0:
-            return np.zeros(0, np.uint8)
-        jobs = []
-        for k, iss in enumerate(self.issuers):
-            lo, hi = slice_bounds(batch.count, k, g)
-            if hi > lo:
-                jobs.append(self._pool.submit(getattr(iss, method), PresentationBatch(batch.kinds, batch.fields[:, lo:hi])))
-        return np.concatenate([j.result() for j in jobs])
+    def _soa(self, fn, batch):
+        import ctypes
+        from . import _binding as B
+        ptrs, keep = B._as_fields(batch.fields)
+        cb = B.afx_presentation_batch(len(batch.kinds), batch.kinds, batch.count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        verdicts = np.zeros(batch.count, np.uint8)
+        self._b.check(fn(self._h, ctypes.byref(cb), verdicts.ctypes.data))
+        return verdicts
 
     def verify_batch(self, batch: PresentationBatch) -> np.ndarray:
         """Batch Issuer::verify: device k verifies items [k*N/G, (k+1)*N/G); verdicts in item order."""
-        return self._fan_out("verify_batch", batch)
+        return self._soa(self._b.L.afx_multi_verify_presentations, batch)
 
     def verify_issuance_batch(self, batch: PresentationBatch) -> np.ndarray:
-        return self._fan_out("verify_issuance_batch", batch)
+        return self._soa(self._b.L.afx_multi_verify_issuances, batch)
+
+    def verify_wire(self, kinds, items, issuance=False) -> np.ndarray:
+        """The same over item-major wire bytes [count][n_fields][32]: each device copies its contiguous byte range."""
+        items = np.ascontiguousarray(items, dtype=np.uint8)
+        kinds = bytes(kinds)
+        nf = (2 * len(kinds) + 9) if issuance else self._b.L.afx_presentation_num_fields(len(kinds), kinds)
+        if items.ndim != 3 or items.shape[1:] != (nf, 32):
+            raise ValueError("items must be [count][%d][32] bytes for this shape" % nf)
+        verdicts = np.zeros(items.shape[0], np.uint8)
+        fn = self._b.L.afx_multi_verify_issuances_wire if issuance else self._b.L.afx_multi_verify_presentations_wire
+        self._b.check(fn(self._h, len(kinds), kinds, items.shape[0], items.ctypes.data, verdicts.ctypes.data))
+        return verdicts
+
+    def issue_batch(self, batch):
+        """Batch Issuer::issue across the devices (request layout of Issuer.issue_batch) -> (IssuanceBatch, status)."""
+        import ctypes
+        from . import _binding as B
+        n, count = len(batch.kinds), batch.count
+        if batch.fields.shape[0] != 3 * n + 14:
+            raise ValueError("a request batch has 3n + 14 fields")
+        ptrs, keep = B._as_fields(batch.fields)
+        cb = B.afx_presentation_batch(n, batch.kinds, count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
+        out = np.zeros((2 * n + 9, count, 32), np.uint8)
+        out[:n] = batch.fields[:n]
+        optrs, okeep = B._as_fields(out[n:])
+        ob = B.afx_issuance_out(ctypes.cast(optrs, ctypes.POINTER(ctypes.c_void_p)), len(okeep))
+        status = np.zeros(count, np.uint8)
+        self._b.check(self._b.L.afx_multi_issue(self._h, ctypes.byref(cb), ctypes.byref(ob), status.ctypes.data))
+        return PresentationBatch(batch.kinds, out), status
 
     def close(self):
-        self._pool.shutdown(wait=True)
-        for iss in self.issuers:
-            iss.close()
+        if getattr(self, "_h", None):
+            self._b.L.afx_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class MixedStream:
+    """Streamed verification of mixed shapes through the library's stream object (afx_stream_*, BASELINE configs[4]): records of
+    several shapes arrive interleaved; the library buckets them by shape into page-locked double buffers and submits every full
+    bucket asynchronously, so bucketing, copies and kernels overlap.  Shapes of different attribute counts belong to different
+    issuers: register each with the `Issuer` that verifies it."""
+
+    def __init__(self, _binding=None):
+        import ctypes
+        if _binding is None:
+            from ._lib import load
+            _binding = load()
+        self._b = _binding
+        h = ctypes.c_void_p()
+        self._b.check(self._b.L.afx_stream_create(ctypes.byref(h)))
+        self._h = h
+        self.record_bytes = []
+        self._keep = []
+
+    def add_shape(self, issuer, kinds, issuance=False) -> int:
+        import ctypes
+        sid, rb = ctypes.c_int(-1), ctypes.c_size_t(0)
+        kinds = bytes(kinds)
+        self._b.check(self._b.L.afx_stream_add_shape(self._h, issuer._h, 1 if issuance else 0, len(kinds), kinds, ctypes.byref(sid), ctypes.byref(rb)))
+        self.record_bytes.append(int(rb.value))
+        self._keep.append(issuer)
+        return int(sid.value)
+
+    def push(self, records, offsets, shape_ids, verdicts):
+        """records: uint8 blob; offsets: uint64 [n] byte offset of each record; shape_ids: uint8 [n]; verdicts: uint8 [n], filled in
+        by the time flush() returns (keep it alive until then)."""
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        shape_ids = np.ascontiguousarray(shape_ids, dtype=np.uint8)
+        if not (verdicts.dtype == np.uint8 and verdicts.flags.c_contiguous and len(verdicts) == len(offsets) == len(shape_ids)):
+            raise ValueError("verdicts must be a contiguous uint8 array with one entry per record")
+        if len(offsets) and int(shape_ids.max()) < len(self.record_bytes):      # an unknown shape id is the library's error to report
+            ends = offsets + np.asarray(self.record_bytes, np.uint64)[shape_ids]
+            if int(ends.max()) > records.size:
+                raise ValueError("a record reaches past the end of the blob")
+        self._keep.append((records, verdicts))
+        self._b.check(self._b.L.afx_stream_push(self._h, records.ctypes.data, offsets.ctypes.data, shape_ids.ctypes.data, len(offsets), verdicts.ctypes.data))
+
+    def flush(self):
+        self._b.check(self._b.L.afx_stream_flush(self._h))
+        self._keep = [k for k in self._keep if not isinstance(k, tuple)]
+
+    @property
+    def buckets_submitted(self):
+        return int(self._b.L.afx_stream_buckets_submitted(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._b.L.afx_stream_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def interleave_records(pools, order):
+    """pools[s]: uint8 [count_s][n_fields_s][32] items of shape s; order: uint8 [total] shape id of every stream position (shape s
+    must occur count_s times) -> (blob, offsets): the stream as one byte blob of variable-length records, in `order`."""
+    order = np.asarray(order, dtype=np.uint8)
+    sizes = np.asarray([p.shape[1] * 32 for p in pools], np.uint64)
+    rec = sizes[order]
+    offsets = np.zeros(len(order), np.uint64)
+    np.cumsum(rec[:-1], out=offsets[1:])
+    blob = np.empty(int(rec.sum()), np.uint8)
+    for sid, p in enumerate(pools):
+        pos = np.nonzero(order == sid)[0]
+        if len(pos) != len(p):
+            raise ValueError("order does not match the pool sizes")
+        w = p.shape[1] * 32
+        # scatter the pool's items to their stream offsets (row gather through an index matrix, chunked to bound memory)
+        flat = p.reshape(len(p), w)
+        for lo in range(0, len(pos), 1 << 16):
+            o = offsets[pos[lo:lo + (1 << 16)]].astype(np.int64)
+            blob[(o[:, None] + np.arange(w, dtype=np.int64)[None, :]).ravel()] = flat[lo:lo + (1 << 16)].ravel()
+    return blob, offsets

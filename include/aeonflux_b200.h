@@ -112,6 +112,11 @@ int afx_verify_issuances(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t*
 int afx_verify_presentations_submit(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, uint64_t* ticket);
 int afx_verify_issuances_submit(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, uint64_t* ticket);
 int afx_wait(afx_ctx* ctx, uint64_t ticket);
+/* The same for item-major wire bytes ([count][n_fields][32], see the *_wire calls below): one host-to-device copy per pass. */
+int afx_verify_presentations_wire_submit(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                                         uint8_t* verdicts, uint64_t* ticket);
+int afx_verify_issuances_wire_submit(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                                     uint8_t* verdicts, uint64_t* ticket);
 
 /* Page-locked host memory for batch buffers (optional: every entry point accepts any host memory).  A host-to-device copy
  * from page-locked memory runs at the full bus rate and asynchronously; from pageable memory the driver stages it at a
@@ -211,6 +216,48 @@ size_t afx_show_num_fields(uint16_t n_attrs, const uint8_t* kinds);
 int afx_show(afx_ctx* ctx, const afx_show_batch* batch, const afx_presentation_out* out, uint8_t* status, afx_debug_dump* dbg);
 int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
                     void* status_dev, void* stream);
+
+/* Several B200s behind one handle -- the `devices[], n_devices` form of SURVEY 8b, so that a caller (the Rust shim's
+ * Issuer::verify_batch) gets the whole box from one call and builds no threads of its own.  afx_multi_create replicates the
+ * issuer context on every listed device (the same arguments as afx_ctx_create; max_batch is per device) and starts one host
+ * thread per device.  A batch call cuts the batch into contiguous item slices -- device k of G takes [k*N/G, (k+1)*N/G), SURVEY
+ * 8e -- runs the single-device entry point on each slice concurrently (a slice longer than max_batch is pipelined in passes, as
+ * there), and every device writes its slice of the caller's verdict array: no collective, nothing but the verdicts is gathered.
+ * Results are identical to the single-device call on the whole batch.  Calls on one handle serialise.
+ * afx_multi_ctx(m, k) is device k's context (owned by the handle) for the per-device calls that have no multi form. */
+typedef struct afx_multi afx_multi;
+int afx_multi_create(const uint8_t* sysparams, size_t sysparams_len, const uint8_t issuer_pub[64], const uint8_t* secret,
+                     size_t secret_len, const int* devices, int n_devices, size_t max_batch, afx_multi** out);
+void afx_multi_destroy(afx_multi* m);
+int afx_multi_num_devices(const afx_multi* m);
+afx_ctx* afx_multi_ctx(afx_multi* m, int k);
+int afx_multi_verify_presentations(afx_multi* m, const afx_presentation_batch* batch, uint8_t* verdicts);
+int afx_multi_verify_presentations_wire(afx_multi* m, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                                        uint8_t* verdicts);
+int afx_multi_verify_issuances(afx_multi* m, const afx_issuance_batch* batch, uint8_t* verdicts);
+int afx_multi_verify_issuances_wire(afx_multi* m, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                                    uint8_t* verdicts);
+int afx_multi_issue(afx_multi* m, const afx_request_batch* batch, const afx_issuance_out* out, uint8_t* status);
+
+/* Streamed verification of MIXED shapes (BASELINE configs[4]; SURVEY 8d config 5: "bucketed by shape into chunks").  A stream is a
+ * sequence of records of several registered shapes, each record the item-major wire bytes of one presentation (issuance = 1: of
+ * one issuance).  Register every shape with the context that verifies it (shapes with different attribute counts belong to
+ * different issuers, hence different contexts; max_batch of the context = the bucket size; give each shape its own context for
+ * full overlap -- shapes sharing one are still correct but take turns).  afx_stream_push takes `n` records: record i is
+ * record_bytes(shape_ids[i]) bytes at records + offsets[i]; it is copied into the page-locked bucket of its shape, and a full
+ * bucket is submitted asynchronously (afx_*_wire_submit) while the shape's second bucket fills, so bucketing, copies and kernels
+ * overlap.  verdicts[i] is written when the record's bucket retires -- at the latest in afx_stream_flush, which submits the
+ * partial buckets and waits for everything; the verdict array of every push must stay valid until then.  The contexts must not
+ * be used for other calls between the first push and the flush.  One thread drives a stream. */
+typedef struct afx_stream afx_stream;
+int afx_stream_create(afx_stream** out);
+void afx_stream_destroy(afx_stream* stream);
+int afx_stream_add_shape(afx_stream* stream, afx_ctx* ctx, int issuance, uint16_t n_attrs, const uint8_t* kinds, int* shape_id,
+                         size_t* record_bytes);
+int afx_stream_push(afx_stream* stream, const uint8_t* records, const uint64_t* offsets, const uint8_t* shape_ids, size_t n,
+                    uint8_t* verdicts);
+int afx_stream_flush(afx_stream* stream);
+uint64_t afx_stream_buckets_submitted(const afx_stream* stream);
 
 /* Primitive self-test (parity hooks for the field / group / scalar code, independent of the protocol flows).  `in` is
  * item-major, `out` is [count][32], ok[i] = 1 unless an input encoding was rejected.

@@ -25,7 +25,6 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <utility>
 #include <vector>
 
@@ -189,42 +188,41 @@ private:
     friend class MultiGpuIssuer;
 };
 
-// One process driving several B200s: a replicated context per device and one host thread per context ("one
-// thread + stream set per GPU").  Device k verifies the contiguous item slice [k*N/G, (k+1)*N/G); nothing but the verdicts is
-// gathered.  The single-process counterpart of bench.py's one-process-per-GPU launch.
+// One process driving several B200s through the C ABI's multi-device handle (afx_multi_*): the library keeps a
+// replicated context and one host thread per device; device k verifies the contiguous item slice [k*N/G, (k+1)*N/G); nothing
+// but the verdicts is gathered.  The single-process counterpart of bench.py's one-process-per-GPU launch.
 class MultiGpuIssuer {
 public:
     MultiGpuIssuer(const std::vector<uint8_t>& system_parameters, const std::vector<uint8_t>& issuer_parameters, const std::vector<uint8_t>& amacs_key,
                    const std::vector<int>& devices, size_t max_batch = 65536) {
         if (devices.empty()) throw std::invalid_argument("at least one device");
-        issuers_.reserve(devices.size());
-        for (int d : devices) issuers_.emplace_back(system_parameters, issuer_parameters, amacs_key, d, max_batch);
+        if (issuer_parameters.size() != 64) throw std::invalid_argument("issuer_parameters must be C_W || I (64 bytes)");
+        int rc = afx_multi_create(system_parameters.data(), system_parameters.size(), issuer_parameters.data(), amacs_key.empty() ? nullptr : amacs_key.data(),
+                                  amacs_key.size(), devices.data(), (int)devices.size(), max_batch, &m_);
+        if (rc != AFX_OK) throw Error(rc);
     }
-    size_t devices() const { return issuers_.size(); }
+    ~MultiGpuIssuer() { if (m_) afx_multi_destroy(m_); }
+    MultiGpuIssuer(const MultiGpuIssuer&) = delete;
+    MultiGpuIssuer& operator=(const MultiGpuIssuer&) = delete;
+    size_t devices() const { return (size_t)afx_multi_num_devices(m_); }
     std::vector<Result<>> verify_batch(const PresentationBatch& p) const {
         if (p.fields.size() != afx_presentation_num_fields((uint16_t)p.kinds.size(), p.kinds.data())) throw std::invalid_argument("wrong number of presentation fields");
-        p.pointers();   // rejects a ragged batch
-        const size_t g = issuers_.size(), n = p.count();
-        std::vector<uint8_t> v(n);
-        std::vector<int> rc(g, AFX_OK);
-        std::vector<std::thread> threads;
-        for (size_t k = 0; k < g; k++) {
-            const size_t lo = k * n / g, hi = (k + 1) * n / g;
-            if (hi == lo) continue;
-            threads.emplace_back([&, k, lo, hi] {
-                std::vector<const uint8_t*> ptrs;
-                for (const auto& f : p.fields) ptrs.push_back(f.data() + 32 * lo);
-                afx_presentation_batch b{(uint16_t)p.kinds.size(), p.kinds.data(), hi - lo, ptrs.data(), ptrs.size()};
-                rc[k] = afx_verify_presentations(issuers_[k].raw(), &b, v.data() + lo, nullptr);
-            });
-        }
-        for (auto& t : threads) t.join();
-        for (int r : rc) if (r != AFX_OK) throw Error(r);
+        auto ptrs = p.pointers();   // rejects a ragged batch
+        afx_presentation_batch b{(uint16_t)p.kinds.size(), p.kinds.data(), p.count(), ptrs.data(), ptrs.size()};
+        std::vector<uint8_t> v(p.count());
+        int rc = afx_multi_verify_presentations(m_, &b, v.data());
+        if (rc != AFX_OK) throw Error(rc);
+        return Issuer::to_results(v);
+    }
+    std::vector<Result<>> verify_wire(const std::vector<uint8_t>& kinds, const uint8_t* items, size_t count) const {
+        std::vector<uint8_t> v(count);
+        int rc = afx_multi_verify_presentations_wire(m_, (uint16_t)kinds.size(), kinds.data(), count, items, v.data());
+        if (rc != AFX_OK) throw Error(rc);
         return Issuer::to_results(v);
     }
 
 private:
-    std::vector<Issuer> issuers_;
+    afx_multi* m_ = nullptr;
 };
 
 // CredentialIssuance::verify (src/issuer.rs:48-57), batch form; needs only the public parameters held by `params`.

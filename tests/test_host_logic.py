@@ -54,7 +54,7 @@ def build_hostemu():
     csrc = os.path.join(ROOT, "aeonflux_b200", "csrc")
     newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc) if not f.endswith(".so"))
     if not os.path.exists(so) or os.path.getmtime(so) < max(newest, os.path.getmtime(src)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-x", "c++", "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-x", "c++", "-o", so, src])
     return so
 
 
