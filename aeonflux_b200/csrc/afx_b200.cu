@@ -377,14 +377,16 @@ static void be_launch_commit_compare(const Workspace& ws, const CmpPair* d_pairs
     k_commit_compare<<<grid_for(ws.count, 256, npairs), 256, 0, s>>>(ws, d_pairs);
 }
 // The whole RLC pass of one chunk: coefficients, column sums, Pippenger, final check.  8 launches.
-static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d_desc, u32 ncterms, const RlcBuffers& rb, be_stream s) {
+static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d_desc, u32 ncterms, const RlcBuffers& rb, be_stream s, be_event* ev_bucket = nullptr) {
     cudaMemsetAsync(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4, s);
     k_rlc_scalars<<<grid_for(ws.count, 128, 1), 128, 0, s>>>(ws, d_desc, rb);
     if (ncterms) k_rlc_colsum<<<ncterms, 256, 0, s>>>(ws, rb);
     k_rlc_digits<<<(rb.N + 255) / 256, 256, 0, s>>>(d_desc, rb, ws.count);
     k_rlc_scan<<<rb.nwin, 1024, 0, s>>>(rb);
     k_rlc_scatter<<<(rb.N + 255) / 256, 256, 0, s>>>(rb);
+    if (ev_bucket) cudaEventRecord(ev_bucket[0], s);
     k_rlc_buckets<<<(rb.nwin * rb.nb + 127) / 128, 128, 0, s>>>(ws, d_desc, rb);
+    if (ev_bucket) cudaEventRecord(ev_bucket[1], s);
     k_rlc_window_reduce<<<rb.nwin, 512, 0, s>>>(rb);
     k_rlc_final<<<1, 32, 0, s>>>(ws, d_desc, rb);
     return 8;

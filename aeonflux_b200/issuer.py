@@ -167,6 +167,29 @@ class Issuer:
         self._b.check(self._b.L.afx_get_stage_times(self._h, ms, 6))
         return dict(zip(self.STAGES, [float(x) for x in ms]))
 
+    def rlc_bucket_time(self):
+        """(ms, points summed, windows) of k_rlc_buckets in the most recent verify_batchable_rlc pass (stage timing must be on)."""
+        ms, n, w = ctypes.c_float(0), ctypes.c_uint64(0), ctypes.c_uint32(0)
+        self._b.check(self._b.L.afx_get_rlc_bucket_time(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)))
+        return float(ms.value), int(n.value), int(w.value)
+
+    def submit_wire(self, kinds, items, issuance=False):
+        """Asynchronous verify of one pass of item-major wire bytes [count][n_fields][32] (count <= max_batch) -> pending result."""
+        items = np.ascontiguousarray(items, dtype=np.uint8)
+        kinds = bytes(kinds)
+        verdicts = np.zeros(items.shape[0], np.uint8)
+        ticket = ctypes.c_uint64(0)
+        fn = self._b.L.afx_verify_issuances_wire_submit if issuance else self._b.L.afx_verify_presentations_wire_submit
+        self._b.check(fn(self._h, len(kinds), kinds, items.shape[0], items.ctypes.data, verdicts.ctypes.data, ctypes.byref(ticket)))
+        issuer = self
+
+        class Pending:
+            def wait(self_inner):
+                issuer._b.check(issuer._b.L.afx_wait(issuer._h, ticket.value))
+                return verdicts
+            _keep = (items,)
+        return Pending()
+
     def _run(self, fn, batch, ncommit, nproofs, debug):
         count = batch.count
         ptrs, keep = B._as_fields(batch.fields)
@@ -239,15 +262,17 @@ class Issuer:
         """Batch CredentialIssuance::verify (issuer.rs:48-57)."""
         return self._run(self._b.L.afx_verify_issuances, batch, 3, 1, debug)
 
-    def issue_batch(self, batch: RequestBatch, debug=False):
+    def issue_batch(self, batch: RequestBatch, debug=False, host_array=None):
         """Batch Issuer::issue (issuer.rs:111-124).  Returns (IssuanceBatch, status): the issuances in the layout
-        verify_issuance_batch takes (attribute[n], t, U, V, challenge, responses[n+5]); status 0 = Ok, 1 = malformed request."""
+        verify_issuance_batch takes (attribute[n], t, U, V, challenge, responses[n+5]); status 0 = Ok, 1 = malformed request.
+        host_array: an allocator such as Issuer.host_array -- the output words then land in page-locked memory (the device-to-host
+        copy of (n + 9) x 32 bytes per item runs at the bus rate instead of through the driver's staging)."""
         n, count = len(batch.kinds), batch.count
         if batch.fields.shape[0] != 3 * n + 14:
             raise ValueError("a request batch has 3n + 14 fields")
         ptrs, keep = B._as_fields(batch.fields)
         cb = B.afx_presentation_batch(n, batch.kinds, count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
-        out = np.zeros((2 * n + 9, count, 32), np.uint8)
+        out = np.zeros((2 * n + 9, count, 32), np.uint8) if host_array is None else host_array((2 * n + 9, count, 32))
         out[:n] = batch.fields[:n]
         optrs, okeep = B._as_fields(out[n:])
         ob = B.afx_issuance_out(ctypes.cast(optrs, ctypes.POINTER(ctypes.c_void_p)), len(okeep))

@@ -283,6 +283,9 @@ uint64_t afx_launch_count(const afx_ctx* ctx);
 #define AFX_NUM_STAGES 6
 void afx_set_stage_timing(afx_ctx* ctx, int on);
 int afx_get_stage_times(afx_ctx* ctx, float* ms, int n);
+/* With stage timing on: device time of the Pippenger bucket-sum kernel (k_rlc_buckets) of the most recent random-linear-combination
+ * pass, the number of per-item points it summed and the number of windows (each point enters one bucket per window). */
+int afx_get_rlc_bucket_time(afx_ctx* ctx, float* ms, uint64_t* inputs, uint32_t* windows);
 
 /* Device time of the most recent *_device / host call's kernel sequence is measured by the caller with events on the
  * stream it passed; this returns the ordinal of the CUDA device the context lives on. */

@@ -49,6 +49,15 @@ def main():
             j = i - min(20, (i + 1) // 3)
             kl.append(kinds); items.append(pres[j])
     vm = sh.verify_mixed(kl, items)
+    # item-major wire bytes, and the same mixed stream as records through the library's stream object (afx_stream_*)
+    vw = sh.verify_wire(kinds, pres)
+    from aeonflux_b200.shard import MixedStream, interleave_records
+    order = np.array([1 if (i % 3 == 2 and i // 3 < 20) else 0 for i in range(count + 20)], np.uint8)
+    blob, offsets = interleave_records([pres, p2], order)
+    ms = MixedStream(_binding=emu)
+    iss2 = Issuer(sp, ip, sk, max_batch=4, _binding=emu)
+    assert [ms.add_shape(sh.issuer, kinds), ms.add_shape(iss2, k2)] == [0, 1]
+    vs = sh.verify_stream(ms, blob, offsets, order)
     if rank == 0:
         ov, _ = orc.verify_presentations(kinds, pres, threads=2)
         ovi, _ = orc.verify_issuances(bytes([0, 0, 2, 2]), issu, threads=2)
@@ -61,6 +70,7 @@ def main():
                 exp_m.append(int(ov[i - min(20, (i + 1) // 3)]))
         json.dump({"world": world, "presentations_ok": bool((v == ov).all()), "rejected": [int(i) for i in np.where(v)[0]],
                    "issuances_ok": bool((vi == ovi).all()), "mixed_ok": bool((vm == np.asarray(exp_m, np.uint8)).all()),
+                   "wire_ok": bool((vw == ov).all()), "stream_ok": bool((vs == np.asarray(exp_m, np.uint8)).all()),
                    "mixed_rejected": int(vm.sum())}, open(out_path, "w"))
     dist.barrier()
     dist.destroy_process_group()

@@ -36,4 +36,6 @@ v, _ = iss.verify_presentations(kinds, pres)
 assert not v.any()
 pres.tofile(os.path.join(HERE, "s16_256.bin"))
 open(os.path.join(HERE, "issuer16.bin"), "wb").write(sp + ip + sk)
+kp = A.SymmetricKeypair.derive(b"aeonflux-b200 bench keypair".ljust(64, b"\0"), A.SystemParameters.from_bytes(sp))
+open(os.path.join(HERE, "keypair16.bin"), "wb").write(R.sc_to_bytes(kp.a) + R.sc_to_bytes(kp.a0) + R.sc_to_bytes(kp.a1) + kp.pk.compress())
 print("wrote", pres.shape, len(sp), len(ip), len(sk))

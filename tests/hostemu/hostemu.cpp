@@ -68,7 +68,7 @@ static void be_launch_ztable(const Workspace& ws, const AmacDesc* d, be_stream) 
 static void be_launch_commit_compare(const Workspace& ws, const CmpPair* pairs, u32 npairs, be_stream) {
     for (u32 k = 0; k < npairs; k++) for (u32 i = 0; i < ws.count; i++) commit_compare_job(ws, pairs[k], i);
 }
-static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d, u32 ncterms, const RlcBuffers& rb, be_stream) {
+static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d, u32 ncterms, const RlcBuffers& rb, be_stream, be_event* = nullptr) {
     std::memset(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4);
     for (u32 i = 0; i < ws.count; i++) rlc_scalars_job(ws, *d, rb, i);
     for (u32 t = 0; t < ncterms; t++) {

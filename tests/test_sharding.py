@@ -53,7 +53,7 @@ def test_sharded_verify_gloo(tmp_path, coracle, world):
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     res = json.load(open(out))
     assert res == {"world": world, "presentations_ok": True, "rejected": [3, 22, 44], "issuances_ok": True, "mixed_ok": True,
-                   "mixed_rejected": 4}
+                   "wire_ok": True, "stream_ok": True, "mixed_rejected": 4}
 
 
 def run_multi_gpu_issuer(coracle, binding, devices, count, max_batch):
