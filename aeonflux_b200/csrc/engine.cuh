@@ -54,7 +54,8 @@ struct MsmDesc {
     ConstTerm con[MAX_CONST_TERMS];
 };
 
-enum : u32 { PJ_COPY = 0, PJ_ADD = 1, PJ_SUB = 2, PJ_UNIFORM = 3 };  // PJ_UNIFORM: from_uniform_bytes(field_a || field_b)
+enum : u32 { PJ_COPY = 0, PJ_ADD = 1, PJ_SUB = 2, PJ_UNIFORM = 3, PJ_OP_MASK = 0xff,   // PJ_UNIFORM: from_uniform_bytes(field_a || field_b)
+              PJ_KEEP_TABLE = 0x100 };  // flag: build the ladder table even when the pass skips tables (ws.no_tables)
 struct PointJob {
     int16_t field_a, field_b;      // input point fields (field_b = -1 for PJ_COPY)
     u16 op;
@@ -248,7 +249,8 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
     u32 w[8];
     ge p;
     u32 ok = 1;
-    if (j.op == PJ_UNIFORM) {       // RistrettoPoint::random: 64 rng bytes through the Elligator map twice (amacs.rs:290)
+    const u32 op = j.op & PJ_OP_MASK;
+    if (op == PJ_UNIFORM) {       // RistrettoPoint::random: 64 rng bytes through the Elligator map twice (amacs.rs:290)
         u32 u[16];
         load8(u, field_ptr(ws, (u32)j.field_a, item)); load8(u + 8, field_ptr(ws, (u32)j.field_b, item));
         p = ge_from_uniform(u);
@@ -256,17 +258,17 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
         load8(w, field_ptr(ws, (u32)j.field_a, item));
         ok = ge_decompress(p, w);
     }
-    if (j.op == PJ_ADD || j.op == PJ_SUB) {
+    if (op == PJ_ADD || op == PJ_SUB) {
         ge q;
         load8(w, field_ptr(ws, (u32)j.field_b, item));
         ok &= ge_decompress(q, w);
-        p = (j.op == PJ_ADD) ? ge_add(p, q) : ge_sub(p, q);
+        p = (op == PJ_ADD) ? ge_add(p, q) : ge_sub(p, q);
     }
     if (!ok) status_or(ws, item, ST_BAD_POINT);
     if (j.ext_slot >= 0) store_ge(ext_ptr(ws, (u32)j.ext_slot, item), p);
     if (j.comp_slot >= 0) { ge_compress(w, p); store8(comp_ptr(ws, (u32)j.comp_slot, item), w); }
     if (j.compneg_slot >= 0) { ge_compress(w, ge_neg(p)); store8(comp_ptr(ws, (u32)j.compneg_slot, item), w); }
-    const bool want_table = j.table_slot >= 0 && !ws.no_tables;
+    const bool want_table = j.table_slot >= 0 && (!ws.no_tables || (j.op & PJ_KEEP_TABLE));
     if (want_table || j.atab_slot >= 0)
         store_table8(want_table ? table_ptr(ws, (u32)j.table_slot, item) : nullptr, p,
                      j.atab_slot >= 0 ? atab_ptr(ws, (u32)j.atab_slot, item) : nullptr);

@@ -139,6 +139,7 @@ struct ShapeProgram {
     std::vector<CmpPair> cmp_pairs;    // (recomputed commitment slot, wire commitment field)
     std::vector<u16> commit_ext;       // extended-coordinates slot of each wire commitment, same order as cmp_pairs' fields
     std::vector<RlcDesc> rlc;          // one descriptor (batchable mode): inputs / constant terms of the random linear combination
+    std::vector<u32> pre_msms;         // batchable mode: MSM jobs whose outputs the transcript absorbs (tU, M_i of an issuance): they run before it
     bool is_issue = false;             // Issuer::issue: constant-schedule MSMs, derived scalars, output words instead of verdicts
     std::vector<DeriveOp> derived;     // per-item derived scalars, slot k = op k
     std::vector<OutWord> out_words;    // prover output words
@@ -226,6 +227,27 @@ inline size_t presentation_num_main_constraints(u32 n, const uint8_t* kinds) {
 inline size_t batchable_num_fields(u32 n, const uint8_t* kinds) {
     size_t hp = 0; for (u32 i = 0; i < n; i++) hp += kinds[i] == 3;
     return presentation_num_fields(n, kinds) - 1 + presentation_num_main_constraints(n, kinds) + 4 * hp;
+}
+
+// BatchableProof mode: the constraints of a compiled shape as inputs of one random linear combination per chunk (engine.cuh, RLC section)
+inline void build_rlc(ShapeProgram& P) {
+    RlcDesc R; std::memset(&R, 0, sizeof R);
+    u32 ni = 0, nt = 0;
+    if (P.cmp_pairs.size() > RLC_MAX_CONS) throw std::length_error("too many constraints");
+    for (size_t j = 0; j < P.cmp_pairs.size(); j++) {
+        const MsmDesc& m = P.msms[P.cmp_pairs[j].commit_slot];
+        R.first_input[j] = (u16)ni; R.first_cterm[j] = (u16)nt;
+        if (ni + m.nvar + 1 > RLC_MAX_INPUTS || nt + m.ncon > RLC_MAX_CTERMS) throw std::length_error("too many RLC terms");
+        for (u32 k = 0; k < m.nvar; k++) {
+            if (m.var[k].ext_slot == 0xffff) throw std::logic_error("ladder base without extended coordinates");
+            R.in_ext[ni] = m.var[k].ext_slot; R.in_neg[ni] = m.var[k].neg; R.in_s[ni] = m.var[k].s; ni++;
+        }
+        R.in_ext[ni] = P.commit_ext[j]; R.in_neg[ni] = 1; R.in_s[ni].op = 0xffff; ni++;      // - rho * R_wire
+        for (u32 k = 0; k < m.ncon; k++) { R.ct_ctab[nt] = m.con[k].ctab; R.ct_neg[nt] = m.con[k].neg; R.ct_s[nt] = m.con[k].s; nt++; }
+    }
+    R.ncons = (u16)P.cmp_pairs.size(); R.ninputs = (u16)ni; R.ncterms = (u16)nt;
+    R.first_input[R.ncons] = (u16)ni; R.first_cterm[R.ncons] = (u16)nt;
+    P.rlc.push_back(R);
 }
 
 // ProofOfValidCredential::verify as a program (presentation.rs:324-443).  batchable = the same statement verified from a
@@ -402,61 +424,60 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         };
         std::stable_sort(P.point_jobs.begin(), P.point_jobs.end(), [&](const PointJob& a, const PointJob& b) { return cost(a) > cost(b); });
     }
-    if (batchable) {   // the same constraints as inputs of one random linear combination per chunk (engine.cuh, RLC section)
-        RlcDesc R; std::memset(&R, 0, sizeof R);
-        u32 ni = 0, nt = 0;
-        if (P.cmp_pairs.size() > RLC_MAX_CONS) throw std::length_error("too many constraints");
-        for (size_t j = 0; j < P.cmp_pairs.size(); j++) {
-            const MsmDesc& m = P.msms[P.cmp_pairs[j].commit_slot];
-            R.first_input[j] = (u16)ni; R.first_cterm[j] = (u16)nt;
-            if (ni + m.nvar + 1 > RLC_MAX_INPUTS || nt + m.ncon > RLC_MAX_CTERMS) throw std::length_error("too many RLC terms");
-            for (u32 k = 0; k < m.nvar; k++) {
-                if (m.var[k].ext_slot == 0xffff) throw std::logic_error("ladder base without extended coordinates");
-                R.in_ext[ni] = m.var[k].ext_slot; R.in_neg[ni] = m.var[k].neg; R.in_s[ni] = m.var[k].s; ni++;
-            }
-            R.in_ext[ni] = P.commit_ext[j]; R.in_neg[ni] = 1; R.in_s[ni].op = 0xffff; ni++;      // - rho * R_wire
-            for (u32 k = 0; k < m.ncon; k++) { R.ct_ctab[nt] = m.con[k].ctab; R.ct_neg[nt] = m.con[k].neg; R.ct_s[nt] = m.con[k].s; nt++; }
-        }
-        R.ncons = (u16)P.cmp_pairs.size(); R.ninputs = (u16)ni; R.ncterms = (u16)nt;
-        R.first_input[R.ncons] = (u16)ni; R.first_cterm[R.ncons] = (u16)nt;
-        P.rlc.push_back(R);
-    }
+    if (batchable) build_rlc(P);
     return P;
 }
 
 // CredentialIssuance::verify as a program (issuer.rs:48-57 -> issuance.rs:132-218).
 // kinds: 0 = scalar attribute (M_i = m_i * G_m[i]), 2 = point attribute.  Fields: attr[n], t, U, V, challenge, responses[n+5].
-inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+// batchable = the same statement verified from a BatchableProof (the commented-out BatchVerifier of issuance.rs:21-22): the
+// challenge word is replaced by the three blinding commitments (constraint order C_W, I, V), i.e. 2n + 11 fields.
+inline size_t issuance_batchable_num_fields(u32 n) { return 2 * (size_t)n + 11; }
+inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const uint8_t* kinds, bool batchable = false) {
     if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
     for (u32 i = 0; i < n; i++) if (kinds[i] != 0 && kinds[i] != 2) throw std::invalid_argument("bad request kind");
     ShapeProgram P;
-    const u32 F_ATTR = 0, F_T = n, F_U = n + 1, F_V = n + 2, F_CHAL = n + 3, F_RESP = n + 4;
-    P.n_fields = 2 * n + 9;
+    P.batchable = batchable;
+    const u32 F_ATTR = 0, F_T = n, F_U = n + 1, F_V = n + 2, F_CHAL = n + 3, F_RESP = n + 4 + (batchable ? 2 : 0);
+    P.n_fields = 2 * n + 9 + (batchable ? 2 : 0);
     // responses: w, w', x_0, x_1, y[n], 1  (issuance.rs:146-159)
     const u32 R_w = F_RESP, R_wp = F_RESP + 1, R_x0 = F_RESP + 2, R_x1 = F_RESP + 3, R_y = F_RESP + 4, R_one = F_RESP + 4 + n;
     for (u32 i = 0; i < n; i++) if (kinds[i] == 0) P.scalar_fields.push_back((u16)(F_ATTR + i));
-    P.scalar_fields.push_back((u16)F_T); P.scalar_fields.push_back((u16)F_CHAL);
+    P.scalar_fields.push_back((u16)F_T);
+    if (!batchable) P.scalar_fields.push_back((u16)F_CHAL);
     for (u32 k = 0; k < n + 5; k++) P.scalar_fields.push_back((u16)(F_RESP + k));
-    u32 ntab = 0;
-    auto table_job = [&](u32 field) { PointJob j; j.field_a = (int16_t)field; j.field_b = -1; j.op = PJ_COPY; j.atab_slot = -1; j.table_slot = (int16_t)ntab; j.ext_slot = -1;
-                                      j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j); return ntab++; };
-    const u32 T_U = table_job(F_U), T_V = table_job(F_V);
+    u32 ntab = 0, next = 0;
+    std::vector<int> tab2ext;
+    // keep_table: U's ladder table feeds tU = t*U, which the transcript absorbs -- it is needed even when the random-linear-combination
+    // pass skips the other tables
+    auto table_job = [&](u32 field, bool keep_table = false) {
+        PointJob j; j.field_a = (int16_t)field; j.field_b = -1; j.op = (u16)(PJ_COPY | (keep_table ? PJ_KEEP_TABLE : 0)); j.atab_slot = -1; j.table_slot = (int16_t)ntab;
+        j.ext_slot = (int16_t)(batchable ? (int)next++ : -1); j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j);
+        tab2ext.push_back(j.ext_slot);
+        return ntab++; };
+    const u32 T_U = table_job(F_U, true), T_V = table_job(F_V);
     std::vector<int> T_M(n, -1);
     for (u32 i = 0; i < n; i++) if (kinds[i] == 2) T_M[i] = (int)table_job(F_ATTR + i);
-    P.n_tables = ntab; P.n_ext = 0; P.n_comp = 0;
-    const ScalarSrc c = sc_field(F_CHAL);
+    if (batchable)       // wire commitments must decode (verify_batchable decompresses them); their extended form feeds the RLC path
+        for (u32 k = 0; k < 3; k++) {
+            PointJob j; j.field_a = (int16_t)(F_CHAL + k); j.field_b = -1; j.op = PJ_COPY; j.atab_slot = -1; j.table_slot = -1; j.ext_slot = (int16_t)next;
+            j.comp_slot = -1; j.compneg_slot = -1; P.point_jobs.push_back(j); P.commit_ext.push_back((u16)next++);
+        }
+    P.n_tables = ntab; P.n_ext = next; P.n_comp = 0;
+    const std::vector<int>* t2e = batchable ? &tab2ext : nullptr;
+    const ScalarSrc c = batchable ? sc_field(SREF_CHAL | 0) : sc_field(F_CHAL);
     u32 slot = 0;
     // derived allocated points that are not inputs: tU = t*U (:180) and M_i = m_i * G_m[i] for scalar attributes (:184)
-    u32 S_tU; { MsmBuilder m(slot); m.var(T_U, sc_field(F_T)); P.msms.push_back(m.d); S_tU = slot++; }
+    u32 S_tU; { MsmBuilder m(slot); m.tab2ext = t2e; m.var(T_U, sc_field(F_T)); P.msms.push_back(m.d); P.pre_msms.push_back(slot); S_tU = slot++; }
     std::vector<int> S_M(n, -1);
-    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) { MsmBuilder m(slot); m.con(ic.id_Gm(i), sc_field(F_ATTR + i)); P.msms.push_back(m.d); S_M[i] = (int)slot++; }
+    for (u32 i = 0; i < n; i++) if (kinds[i] == 0) { MsmBuilder m(slot); m.con(ic.id_Gm(i), sc_field(F_ATTR + i)); P.msms.push_back(m.d); P.pre_msms.push_back(slot); S_M[i] = (int)slot++; }
     // constraints (:195-215)
     u32 S_CW, S_I, S_V;
     { MsmBuilder m(slot); m.con(ic.id_Gw(), sc_field(R_w)); m.con(ic.id_Gwp(), sc_field(R_wp)); m.con(ic.id_CW(), c, true); P.msms.push_back(m.d); S_CW = slot++; }
     { MsmBuilder m(slot); m.con(ic.id_GV(), sc_field(R_one)); m.con(ic.id_Gx0(), sc_field(R_x0), true); m.con(ic.id_Gx1(), sc_field(R_x1), true);
       for (u32 i = 0; i < n; i++) m.con(ic.id_Gy(i), sc_field(R_y + i), true);
       m.con(ic.id_I(), c, true); P.msms.push_back(m.d); S_I = slot++; }
-    { MsmBuilder m(slot); m.con(ic.id_Gw(), sc_field(R_w));
+    { MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_Gw(), sc_field(R_w));
       m.var(T_U, sc_muladd3(R_x0, R_x1, F_T));               // x_0*U + x_1*(t*U) = (x_0 + x_1*t)*U
       for (u32 i = 0; i < n; i++) {
           if (kinds[i] == 0) m.con(ic.id_Gm(i), sc_mul2(R_y + i, F_ATTR + i));  // y_i * (m_i*G_m[i])
@@ -474,12 +495,18 @@ inline ShapeProgram compile_issuance_verify(const IssuerConsts& ic, u32 n, const
     tb.point_var_const("C_W", ic.enc[ic.id_CW()].data()); tb.point_var_const("I", ic.enc[ic.id_I()].data());
     tb.point_var("U", SRC_FIELD, F_U); tb.point_var("V", SRC_FIELD, F_V); tb.point_var("tU", SRC_COMMIT, S_tU);
     for (u32 i = 0; i < n; i++) { if (kinds[i] == 0) tb.point_var("M", SRC_COMMIT, (u32)S_M[i]); else tb.point_var("M", SRC_FIELD, F_ATTR + i); }
-    tb.blinding_commitment("C_W", S_CW); tb.blinding_commitment("I", S_I); tb.blinding_commitment("V", S_V);
-    for (u32 s : {S_CW, S_I, S_V}) P.dump_commit.push_back(s);
+    const char* labels[3] = {"C_W", "I", "V"};
+    const u32 slots[3] = {S_CW, S_I, S_V};
+    for (u32 k = 0; k < 3; k++) {
+        if (batchable) { tb.blinding_commitment_wire(labels[k], F_CHAL + k); CmpPair cp; cp.commit_slot = (u16)slots[k]; cp.field = (u16)(F_CHAL + k); P.cmp_pairs.push_back(cp); }
+        else tb.blinding_commitment(labels[k], slots[k]);
+        P.dump_commit.push_back(slots[k]);
+    }
     tb.challenge();
-    finish_transcript(P, tb, F_CHAL, 0);
+    finish_transcript(P, tb, batchable ? 0xffff : F_CHAL, 0);
     P.n_msm = slot; P.n_proofs = 1;
     mark_comb_jobs(P);
+    if (batchable) build_rlc(P);
     return P;
 }
 

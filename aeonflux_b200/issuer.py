@@ -262,17 +262,20 @@ class Issuer:
         """Batch CredentialIssuance::verify (issuer.rs:48-57)."""
         return self._run(self._b.L.afx_verify_issuances, batch, 3, 1, debug)
 
-    def issue_batch(self, batch: RequestBatch, debug=False, host_array=None):
+    def issue_batch(self, batch: RequestBatch, debug=False, out=None):
         """Batch Issuer::issue (issuer.rs:111-124).  Returns (IssuanceBatch, status): the issuances in the layout
         verify_issuance_batch takes (attribute[n], t, U, V, challenge, responses[n+5]); status 0 = Ok, 1 = malformed request.
-        host_array: an allocator such as Issuer.host_array -- the output words then land in page-locked memory (the device-to-host
-        copy of (n + 9) x 32 bytes per item runs at the bus rate instead of through the driver's staging)."""
+        out: optional preallocated uint8 [2n + 9][count][32] array for the result, e.g. from Issuer.host_array -- in page-locked
+        memory the device-to-host copy of (n + 9) x 32 bytes per item runs at the bus rate instead of through the driver's staging."""
         n, count = len(batch.kinds), batch.count
         if batch.fields.shape[0] != 3 * n + 14:
             raise ValueError("a request batch has 3n + 14 fields")
         ptrs, keep = B._as_fields(batch.fields)
         cb = B.afx_presentation_batch(n, batch.kinds, count, ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)), len(keep))
-        out = np.zeros((2 * n + 9, count, 32), np.uint8) if host_array is None else host_array((2 * n + 9, count, 32))
+        if out is None:
+            out = np.zeros((2 * n + 9, count, 32), np.uint8)
+        elif out.shape != (2 * n + 9, count, 32) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint8 [2n + 9][count][32] array")
         out[:n] = batch.fields[:n]
         optrs, okeep = B._as_fields(out[n:])
         ob = B.afx_issuance_out(ctypes.cast(optrs, ctypes.POINTER(ctypes.c_void_p)), len(okeep))

@@ -371,7 +371,8 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     kern = stage_fracs(issuer4, im, B, imad_peak, ("k_points", "k_msm_ct"))
     issuer4.set_stage_timing(False)
     rb = RequestBatch(kinds, rq)
-    e2e_s, (issued, st) = time_wall(lambda: issuer4.issue_batch(rb, host_array=issuer4.host_array), steps)
+    issued_host = issuer4.host_array((2 * n + 9, B, 32))
+    e2e_s, (issued, st) = time_wall(lambda: issuer4.issue_batch(rb, out=issued_host), steps)
     assert not st.any()
     orc = C.Issuer(sp4, ip4, sk4)
     sample = min(B, cores * 1024)
