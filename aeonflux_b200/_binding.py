@@ -34,7 +34,8 @@ class Binding:
                "afx_multi_create", "afx_multi_destroy", "afx_multi_num_devices", "afx_multi_ctx", "afx_multi_verify_presentations",
                "afx_multi_verify_presentations_wire", "afx_multi_verify_issuances", "afx_multi_verify_issuances_wire", "afx_multi_issue",
                "afx_verify_presentations_wire_submit", "afx_verify_issuances_wire_submit", "afx_stream_create", "afx_stream_destroy",
-               "afx_stream_add_shape", "afx_stream_push", "afx_stream_flush", "afx_stream_buckets_submitted"]
+               "afx_stream_add_shape", "afx_stream_push", "afx_stream_flush", "afx_stream_buckets_submitted",
+               "afx_issue_wire", "afx_show_wire", "afx_issuance_batchable_num_fields", "afx_verify_issuances_batchable", "afx_verify_issuances_batchable_rlc", "afx_get_rlc_stats"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -69,6 +70,14 @@ class Binding:
         L.afx_verify_presentations_batchable.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(afx_debug_dump)]
         L.afx_verify_presentations_batchable_rlc.restype = ctypes.c_int
         L.afx_verify_presentations_batchable_rlc.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, vp, ctypes.POINTER(ctypes.c_uint32)]
+        L.afx_issuance_batchable_num_fields.restype = sz
+        L.afx_issuance_batchable_num_fields.argtypes = [ctypes.c_uint16]
+        L.afx_verify_issuances_batchable.restype = ctypes.c_int
+        L.afx_verify_issuances_batchable.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(afx_debug_dump)]
+        L.afx_verify_issuances_batchable_rlc.restype = ctypes.c_int
+        L.afx_verify_issuances_batchable_rlc.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, vp, ctypes.POINTER(ctypes.c_uint32)]
+        L.afx_get_rlc_stats.restype = ctypes.c_int
+        L.afx_get_rlc_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         for f in ("afx_verify_presentations_wire", "afx_verify_issuances_wire"):
             getattr(L, f).restype = ctypes.c_int
             getattr(L, f).argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp]
@@ -84,6 +93,9 @@ class Binding:
         L.afx_show.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), ctypes.POINTER(afx_issuance_out), vp, ctypes.POINTER(afx_debug_dump)]
         L.afx_show_device.restype = ctypes.c_int
         L.afx_show_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp, vp]
+        for f in ("afx_issue_wire", "afx_show_wire"):
+            getattr(L, f).restype = ctypes.c_int
+            getattr(L, f).argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp]
         L.afx_selftest_primitive.restype = ctypes.c_int
         L.afx_selftest_primitive.argtypes = [vp, ctypes.c_int, vp, sz, vp, vp]
         L.afx_launch_count.restype = ctypes.c_uint64

@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <sys/random.h>
 
 #include "engine.cuh"
 
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(256) k_commit_compare(Workspace ws, const CmpP
 
 // ---- random-linear-combination path (BatchableProof): coefficients, Pippenger bucket method, final check -------------------
 __global__ void __launch_bounds__(128) k_rlc_scalars(Workspace ws, const RlcDesc* d, RlcBuffers rb) {
-    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < ws.count) rlc_scalars_job(ws, *d, rb, item);
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rb.cnt) rlc_scalars_job(ws, *d, rb, rb.lo + i);
 }
 // one CTA per constant term: chunk-wide sum of its coefficients mod l (9-word partial sums, shared-memory tree)
 __global__ void __launch_bounds__(256) k_rlc_colsum(Workspace ws, RlcBuffers rb) {
@@ -149,8 +150,8 @@ __global__ void __launch_bounds__(256) k_rlc_colsum(Workspace ws, RlcBuffers rb)
     const u32 t = blockIdx.x;
     u32 acc[9];
     for (int i = 0; i < 9; i++) acc[i] = 0;
-    for (u32 item = threadIdx.x; item < ws.count; item += blockDim.x) {
-        u32 v[8]; load8(v, rb.cterm + ((size_t)t * ws.count + item) * 8);
+    for (u32 item = threadIdx.x; item < rb.cnt; item += blockDim.x) {
+        u32 v[8]; load8(v, rb.cterm + ((size_t)t * rb.cnt + item) * 8);
         rlc_add288(acc, v);
     }
     for (int i = 0; i < 9; i++) part[threadIdx.x][i] = acc[i];
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(256) k_rlc_colsum(Workspace ws, RlcBuffers rb)
     }
     if (threadIdx.x == 0) { sc r = rlc_reduce288(part[0]); for (int i = 0; i < 8; i++) rb.csum[8 * t + i] = r.v[i]; }
 }
-__global__ void __launch_bounds__(256) k_rlc_digits(const RlcDesc* d, RlcBuffers rb, u32 count) {
+__global__ void __launch_bounds__(256) k_rlc_digits(const RlcDesc* d, RlcBuffers rb) {
     u32 n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < rb.N) rlc_digits_job(*d, rb, count, n);
+    if (n < rb.N) rlc_digits_job(*d, rb, n);
 }
 // one CTA per window: exclusive scan of the 2^(c-1) bucket sizes (each thread owns a run of consecutive buckets; the run
 // totals are scanned in shared memory), offsets written in place and copied to the scatter cursors
@@ -292,6 +293,7 @@ static int be_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 16) != c
 static void be_free(void* p) { cudaFree(p); }
 static int be_h2d(void* d, const void* h, size_t n, be_stream s) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) != cudaSuccess; }
 static int be_d2h(void* h, const void* d, size_t n, be_stream s) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess; }
+static int be_d2d(void* d, const void* src, size_t n, be_stream s) { return cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess; }
 static int be_memset(void* d, int v, size_t n, be_stream s) { return cudaMemsetAsync(d, v, n, s) != cudaSuccess; }
 static int be_sync(be_stream s) { return cudaStreamSynchronize(s) != cudaSuccess; }
 static int be_check_launch() {
@@ -299,6 +301,7 @@ static int be_check_launch() {
     if (e != cudaSuccess) { std::fprintf(stderr, "aeonflux_b200: CUDA launch failed: %s\n", cudaGetErrorString(e)); return -3; }
     return 0;
 }
+static int be_os_random(void* p, size_t n) { return getrandom(p, n, 0) != (ssize_t)n; }
 typedef cudaEvent_t be_event;
 static void be_event_create(be_event* e) { cudaEventCreate(e); }
 static void be_event_destroy(be_event e) { cudaEventDestroy(e); }
@@ -379,9 +382,9 @@ static void be_launch_commit_compare(const Workspace& ws, const CmpPair* d_pairs
 // The whole RLC pass of one chunk: coefficients, column sums, Pippenger, final check.  8 launches.
 static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d_desc, u32 ncterms, const RlcBuffers& rb, be_stream s, be_event* ev_bucket = nullptr) {
     cudaMemsetAsync(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4, s);
-    k_rlc_scalars<<<grid_for(ws.count, 128, 1), 128, 0, s>>>(ws, d_desc, rb);
+    k_rlc_scalars<<<grid_for(rb.cnt, 128, 1), 128, 0, s>>>(ws, d_desc, rb);
     if (ncterms) k_rlc_colsum<<<ncterms, 256, 0, s>>>(ws, rb);
-    k_rlc_digits<<<(rb.N + 255) / 256, 256, 0, s>>>(d_desc, rb, ws.count);
+    k_rlc_digits<<<(rb.N + 255) / 256, 256, 0, s>>>(d_desc, rb);
     k_rlc_scan<<<rb.nwin, 1024, 0, s>>>(rb);
     k_rlc_scatter<<<(rb.N + 255) / 256, 256, 0, s>>>(rb);
     if (ev_bucket) cudaEventRecord(ev_bucket[0], s);

@@ -112,6 +112,7 @@ struct Workspace {
     u32* chal;           // [n_proofs][count][8]  recomputed challenges
     u32* status;         // [count]   0 = ok so far
     u32* derived;        // [n_derived][count][8]  per-item derived scalars (Issuer::issue only)
+    u32 os_word, os_item, os_base;   // prover output strides in 32-byte words: struct-of-arrays (count, 1, 0) or item-major (1, words per item, first word)
     // per-issuer constants
     const u32* ctabs;    // [n_ctab][2048][24]   affine Niels multiples 1..2048
     const u32* ctabs16;  // [n_ctab][32768][24]  multiples 1..32768, or null (the verify-path MSMs then use radix 4096)
@@ -525,6 +526,9 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
             u32 word = scratch[(k * 8 + (i >> 3)) * scratch_stride];
             int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
             pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].table_slot, item), dig, d.var[k].neg);
+#ifndef AFX_NO_CT_PREFETCH
+            prefetch_atab(atab_ptr(ws, d.var[k + 1 < d.nvar ? k + 1 : 0].table_slot, item & ~31u));   // next scan, hidden behind this add
+#endif
             GE_LADDER_ADD(cacc, e);
         }
         for (u32 k = 0; k < d.ncon; k++) {
@@ -580,7 +584,7 @@ AFX_HD void out_word_job(const Workspace& ws, const OutWord& d, u32 word, u32 it
         sc r = sc_muladd(s, c, b);
         for (int i = 0; i < 8; i++) w[i] = r.v[i];
     }
-    store8(out + ((size_t)word * ws.count + item) * 8, w);
+    store8(out + ((size_t)word * ws.os_word + (size_t)item * ws.os_item + ws.os_base) * 8, w);
 }
 
 // ---- stage: commitment comparison (BatchableProof, exact path) -------------------------------------------------------
@@ -622,7 +626,8 @@ struct RlcBuffers {
     u32* buckets;   // [nwin][nb][32]        bucket sums (extended coordinates)
     u32* wsum;      // [nwin][32]            per-window sums
     u32* result;    // [9]                   compress(total) and the verdict word
-    u32 N, nwin, c, nb;    // inputs in the chunk, windows, window bits, buckets per window = 2^(c-1)
+    u32 N, nwin, c, nb;    // inputs of the pass, windows, window bits, buckets per window = 2^(c-1)
+    u32 lo, cnt;           // the pass covers items [lo, lo + cnt) of the chunk (bisection of a chunk whose combination did not vanish); N = cnt * ninputs
     u64 seed[4];
 };
 
@@ -641,7 +646,7 @@ AFX_HD sc rlc_rho(const u64* st, u32 j) {
     r.v[0] = (u32)lo; r.v[1] = (u32)(lo >> 32); r.v[2] = (u32)hi; r.v[3] = (u32)(hi >> 32) & 0x7fffffffu;
     return r;
 }
-// one thread per item: the coefficient of every input and constant term
+// one thread per item (absolute index in [lo, lo + cnt)): the coefficient of every input and constant term
 AFX_HD void rlc_scalars_job(const Workspace& ws, const RlcDesc& d, const RlcBuffers& rb, u32 item) {
     u64 st[25];
     for (u32 j = 0; j < d.ncons; j++) {
@@ -651,12 +656,12 @@ AFX_HD void rlc_scalars_job(const Workspace& ws, const RlcDesc& d, const RlcBuff
             // the sign of an input is applied to its point in the bucket pass, not to the scalar: -rho mod l would share its
             // upper ~125 bits with every other 128-bit rho and pile all those inputs into the same few buckets
             sc v = d.in_s[k].op == 0xffff ? rho : sc_mul(rho, eval_scalar(ws, d.in_s[k], item));
-            store8(rb.scal + ((size_t)k * ws.count + item) * 8, v.v);
+            store8(rb.scal + ((size_t)k * rb.cnt + (item - rb.lo)) * 8, v.v);
         }
         for (u32 t = d.first_cterm[j]; t < d.first_cterm[j + 1]; t++) {
             sc v = sc_mul(rho, eval_scalar(ws, d.ct_s[t], item));
             if (d.ct_neg[t]) v = sc_neg(v);
-            store8(rb.cterm + ((size_t)t * ws.count + item) * 8, v.v);
+            store8(rb.cterm + ((size_t)t * rb.cnt + (item - rb.lo)) * 8, v.v);
         }
     }
 }
@@ -676,9 +681,9 @@ AFX_HD sc rlc_reduce288(const u32* acc) {
     return sc_reduce512(x);
 }
 // signed base-2^c digits of a canonical scalar: digit w in [-2^(c-1), 2^(c-1)]
-AFX_HD void rlc_digits_job(const RlcDesc& d, const RlcBuffers& rb, u32 count, u32 n) {
+AFX_HD void rlc_digits_job(const RlcDesc& d, const RlcBuffers& rb, u32 n) {
     u32 v[9]; load8(v, rb.scal + (size_t)n * 8); v[8] = 0;
-    const u32 flip = d.in_neg[n / count] & 1u;
+    const u32 flip = d.in_neg[n / rb.cnt] & 1u;
     u32 carry = 0;
     const u32 half = 1u << (rb.c - 1), mask = (1u << rb.c) - 1u;
     for (u32 w = 0; w < rb.nwin; w++) {
@@ -726,7 +731,7 @@ AFX_HD void rlc_bucket_job(const Workspace& ws, const RlcDesc& d, const RlcBuffe
     ge acc = ge_identity();
     for (u32 q = lo; q < hi; q++) {
         u32 e = rb.sorted[(size_t)w * rb.N + q], n = e >> 1;
-        u32 k = n / ws.count, item = n - k * ws.count;
+        u32 k = n / rb.cnt, item = rb.lo + (n - k * rb.cnt);
         ge p = load_ge(ext_ptr(ws, d.in_ext[k], item));
         if (e & 1u) p = ge_neg(p);
         acc = ge_add(acc, p);

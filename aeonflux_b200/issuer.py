@@ -232,10 +232,10 @@ class Issuer:
         include/aeonflux_b200.h): every constraint of every item is checked exactly."""
         return self._run(self._b.L.afx_verify_presentations_batchable, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
 
-    def verify_batchable_rlc(self, batch: PresentationBatch, seed: bytes):
-        """BatchableProof presentations checked as one random linear combination per chunk (Pippenger over the whole chunk), with
-        the exact check as fallback for a chunk that does not vanish.  seed: 32 bytes unpredictable to the provers.
-        Returns (verdicts, number of chunks that fell back)."""
+    def verify_batchable_rlc(self, batch: PresentationBatch, seed: bytes, issuance=False):
+        """BatchableProof presentations (or issuances) checked as one random linear combination per chunk (Pippenger over the whole
+        chunk); a chunk that does not vanish is bisected down to 1,024-item leaves, which are re-verified exactly.  seed: 32 bytes
+        (the library mixes in a nonce of its own).  Returns (verdicts, number of chunks that needed exact work)."""
         if len(seed) != 32:
             raise ValueError("seed must be 32 bytes")
         ptrs, keep = B._as_fields(batch.fields)
@@ -243,8 +243,20 @@ class Issuer:
         verdicts = np.zeros(batch.count, np.uint8)
         sd = ctypes.create_string_buffer(bytes(seed), 32)
         fell_back = ctypes.c_uint32(0)
-        self._b.check(self._b.L.afx_verify_presentations_batchable_rlc(self._h, ctypes.byref(cb), ctypes.addressof(sd), verdicts.ctypes.data, ctypes.byref(fell_back)))
+        fn = self._b.L.afx_verify_issuances_batchable_rlc if issuance else self._b.L.afx_verify_presentations_batchable_rlc
+        self._b.check(fn(self._h, ctypes.byref(cb), ctypes.addressof(sd), verdicts.ctypes.data, ctypes.byref(fell_back)))
         return verdicts, int(fell_back.value)
+
+    def verify_issuance_batchable(self, batch: IssuanceBatch, debug=False):
+        """Batch CredentialIssuance::verify for issuances whose proof is a BatchableProof: fields attribute[n], t, U, V,
+        commitments[3], responses[n + 5]; every constraint checked exactly."""
+        return self._run(self._b.L.afx_verify_issuances_batchable, batch, 3, 1, debug)
+
+    def rlc_stats(self):
+        """(combination passes run, items re-verified exactly) by the *_rlc calls on this context so far."""
+        a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self._b.check(self._b.L.afx_get_rlc_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     def verify_wire(self, kinds, items, issuance=False):
         """Batch Issuer::verify (or CredentialIssuance::verify) over item-major wire bytes: items = uint8 [count][n_fields][32],
@@ -314,6 +326,38 @@ class Issuer:
         self._b.check(self._b.L.afx_show(self._h, ctypes.byref(cb), ctypes.byref(ob), status.ctypes.data, ctypes.byref(dbg) if dbg is not None else None))
         res = PresentationBatch(kinds, out)
         return (res, status, dump) if debug else (res, status)
+
+    def issue_wire(self, kinds, requests, out=None):
+        """Batch Issuer::issue over item-major requests uint8 [count][3n + 14][32] -> (issuances uint8 [count][2n + 9][32] in the
+        layout verify_wire(issuance=True) takes, status).  out: optional preallocated (e.g. page-locked) result array."""
+        kinds = bytes(kinds)
+        n = len(kinds)
+        requests = np.ascontiguousarray(requests, dtype=np.uint8)
+        if requests.ndim != 3 or requests.shape[1:] != (3 * n + 14, 32):
+            raise ValueError("requests must be [count][3n + 14][32] bytes")
+        count = requests.shape[0]
+        if out is None:
+            out = np.zeros((count, 2 * n + 9, 32), np.uint8)
+        elif out.shape != (count, 2 * n + 9, 32) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint8 [count][2n + 9][32] array")
+        status = np.zeros(count, np.uint8)
+        self._b.check(self._b.L.afx_issue_wire(self._h, n, kinds, count, requests.ctypes.data, out.ctypes.data, status.ctypes.data))
+        return out, status
+
+    def show_wire(self, kinds, inputs, out=None):
+        """Batch AnonymousCredential::show over item-major inputs uint8 [count][afx_show_num_fields][32] -> (presentations uint8
+        [count][n_fields][32] in the layout verify_wire takes, status)."""
+        kinds = bytes(kinds)
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        nf = self._b.L.afx_show_num_fields(len(kinds), kinds)
+        if inputs.ndim != 3 or inputs.shape[1:] != (nf, 32):
+            raise ValueError("inputs must be [count][%d][32] bytes for this shape" % nf)
+        count = inputs.shape[0]
+        if out is None:
+            out = np.zeros((count, self.num_fields(kinds), 32), np.uint8)
+        status = np.zeros(count, np.uint8)
+        self._b.check(self._b.L.afx_show_wire(self._h, len(kinds), kinds, count, inputs.ctypes.data, out.ctypes.data, status.ctypes.data))
+        return out, status
 
     def show_batch_device(self, kinds, count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream=0):
         self._b.check(self._b.L.afx_show_device(self._h, len(kinds), bytes(kinds), count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream))

@@ -136,14 +136,28 @@ void afx_host_free(void* p);
  * must satisfy sum resp_k*P_k - c*LHS == commitment.  The aMAC recomputation of Z is unchanged (constant schedule).
  *   afx_verify_presentations_batchable      checks every constraint of every item exactly (one MSM per constraint);
  *   afx_verify_presentations_batchable_rlc  checks one random linear combination of all constraints of all items of a chunk as
- *       a single Pippenger multiscalar multiplication (128-bit coefficients derived from `seed`, which must be unpredictable to
- *       the provers), and falls back to the exact check for a chunk whose combination does not vanish -- so the verdicts are
- *       the exact ones except with probability ~2^-120 per chunk; fast when rejects are rare. */
+ *       a single Pippenger multiscalar multiplication.  A chunk whose combination does not vanish is bisected: its halves get fresh
+ *       coefficients and their own pass, down to leaves of 1,024 items, which are re-verified exactly; after 16 failing nodes, or
+ *       when the suspect leaves cover more than half the chunk, the rest is checked exactly.  So the verdicts are the exact ones
+ *       except with probability ~2^-120 per pass; one bad item in a chunk costs a few small passes and one leaf, many bad items
+ *       cost the exact check plus a bounded number of wasted passes (fast when rejects are rare).
+ *       Coefficients: 127 bits each, derived from `seed` AND a nonce the library draws from the operating system for every call,
+ *       so they are unpredictable to the provers even if a caller reuses or mis-generates its seed (pass 32 zero bytes if you have
+ *       nothing better; the seed only adds entropy).
+ * The same two calls exist for issuances (afx_verify_issuances_batchable{,_rlc}: the BatchVerifier the reference left commented out
+ * at src/nizk/issuance.rs:21-22): fields attribute[n], t, U, V, commitments[3] (constraint order C_W, I, V), responses[n + 5],
+ * i.e. afx_issuance_batchable_num_fields(n) = 2n + 11 words. */
 size_t afx_batchable_num_fields(uint16_t n_attrs, const uint8_t* kinds);
 int afx_verify_presentations_batchable(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
-/* exact_chunks (nullable): how many chunks of max_batch items had to fall back to the exact check. */
+/* exact_chunks (nullable): how many chunks of max_batch items held a combination that did not vanish (and needed exact work). */
 int afx_verify_presentations_batchable_rlc(afx_ctx* ctx, const afx_presentation_batch* batch, const uint8_t seed[32], uint8_t* verdicts,
                                            uint32_t* exact_chunks);
+size_t afx_issuance_batchable_num_fields(uint16_t n_attrs);
+int afx_verify_issuances_batchable(afx_ctx* ctx, const afx_issuance_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
+int afx_verify_issuances_batchable_rlc(afx_ctx* ctx, const afx_issuance_batch* batch, const uint8_t seed[32], uint8_t* verdicts,
+                                       uint32_t* exact_chunks);
+/* Cumulative counters of the *_rlc calls on this context: combination passes run, items re-verified exactly. */
+int afx_get_rlc_stats(afx_ctx* ctx, uint64_t* rlc_passes, uint64_t* exact_items);
 
 /* Item-major ("wire") variants.  The reference defines no serialization for a presentation or an issuance
  * (src/nizk/presentation.rs:117 "XXX"); the natural one is the concatenation of the item's 32-byte words in
@@ -196,6 +210,14 @@ int afx_issue(afx_ctx* ctx, const afx_request_batch* batch, const afx_issuance_o
 int afx_issue_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
                      void* status_dev, void* stream);
 
+/* Item-major ("wire") form of afx_issue: a CredentialRequest (src/user.rs:137-139) travels as the concatenation of its words --
+ * attribute[n] followed by the rng halves, 3n + 14 words -- and a batch as the concatenation of its requests,
+ *     requests = [count][3n + 14][32];   issuances = [count][2n + 9][32]: attribute[n] (echoed), t, U, V, challenge, responses[n + 5]
+ * i.e. each issuance comes back in exactly the layout afx_verify_issuances_wire takes.  One copy each way per pass of max_batch
+ * items.  status as afx_issue (a malformed request gives status 1 and an all-zero issuance). */
+int afx_issue_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* requests, uint8_t* issuances,
+                   uint8_t* status);
+
 /* Batch AnonymousCredential::show (src/credential.rs:37-46 = ProofOfValidCredential::prove, src/nizk/presentation.rs:139-321, plus
  * one ProofOfEncryption::prove, src/nizk/encryption.rs:58-142, with Keypair::encrypt, src/symmetric.rs:252-261, per hidden
  * plaintext attribute).  The USER-side batch operation: it needs no issuer secret, so a context created with
@@ -216,6 +238,10 @@ size_t afx_show_num_fields(uint16_t n_attrs, const uint8_t* kinds);
 int afx_show(afx_ctx* ctx, const afx_show_batch* batch, const afx_presentation_out* out, uint8_t* status, afx_debug_dump* dbg);
 int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const void* fields_dev, void* out_dev,
                     void* status_dev, void* stream);
+/* Item-major form: inputs = [count][afx_show_num_fields][32], presentations = [count][afx_presentation_num_fields][32] -- what
+ * afx_verify_presentations_wire takes. */
+int afx_show_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* inputs, uint8_t* presentations,
+                  uint8_t* status);
 
 /* Several B200s behind one handle -- the `devices[], n_devices` form of SURVEY 8b, so that a caller (the Rust shim's
  * Issuer::verify_batch) gets the whole box from one call and builds no threads of its own.  afx_multi_create replicates the

@@ -325,9 +325,10 @@ def issuance_prove(issuer, amac, attrs, blindings):
     return (c, responses), commitments
 
 
-def issuance_verify(proof, sp, ip, amac, attrs, trace=None):
+def issuance_verify(proof, sp, ip, amac, attrs, trace=None, batchable=False):
     """ProofOfIssuance::verify, issuance.rs:132-218 (via CredentialIssuance::verify, issuer.rs:48-57).
-    Raises VerificationFailure."""
+    Raises VerificationFailure.  batchable: proof = (commitments[3], responses), checked with zkp's verify_batchable (the
+    BatchVerifier route the reference left commented out, issuance.rs:21-22)."""
     c, responses = proof
     t = Transcript(b"2019/1416 anonymous credential")
     vf = Verifier(b"2019/1416 issuance proof", t)
@@ -354,7 +355,10 @@ def issuance_verify(proof, sp, ip, amac, attrs, trace=None):
     vf.constrain(C_W, [(w, G_w), (w_prime, G_w_prime)])
     vf.constrain(I, [(one, G_V), (x_0, neg_G_x_0), (x_1, neg_G_x_1)] + list(zip(y, neg_G_y)))
     vf.constrain(V, [(w, G_w), (x_0, U), (x_1, tU)] + list(zip(y, M)))
-    vf.verify_compact(c, responses)
+    if batchable:
+        vf.verify_batchable(c, responses)
+    else:
+        vf.verify_compact(c, responses)
 
 
 # ---- credential.rs -------------------------------------------------------------

@@ -172,23 +172,24 @@ def request_kinds(attrs):
     return bytes(KIND_PS if k in ("PS", "SS") else KIND_PP for k, _ in attrs)
 
 
-def verify_issuance_flat(sp, ip, kinds, words):
-    """-> (verdict, trace) for CredentialIssuance::verify (issuer.rs:48-57)."""
+def verify_issuance_flat(sp, ip, kinds, words, batchable=False):
+    """-> (verdict, trace) for CredentialIssuance::verify (issuer.rs:48-57).  batchable: the challenge word is replaced by the three
+    blinding commitments (C_W, I, V)."""
     kinds = list(kinds)
     n = len(kinds)
     out = {"commitments": [], "challenges": []}
     trace = {}
     verdict = 0
     try:
-        if len(words) != issuance_num_words(n):
+        if len(words) != issuance_num_words(n) + (2 if batchable else 0):
             raise ValueError("malformed: word count")
         attrs = []
         for k, b in zip(kinds, words[:n]):
             attrs.append(("PS", _sc(b)) if k == KIND_PS else ("PP", _pt(b)))
         t, U, V = _sc(words[n]), _pt(words[n + 1]), _pt(words[n + 2])
-        c = _sc(words[n + 3])
-        resp = [_sc(b) for b in words[n + 4:]]
-        issuance_verify((c, resp), sp, ip, Amac(t, U, V), attrs, trace)
+        c = list(words[n + 3:n + 6]) if batchable else _sc(words[n + 3])
+        resp = [_sc(b) for b in words[n + (6 if batchable else 4):]]
+        issuance_verify((c, resp), sp, ip, Amac(t, U, V), attrs, trace, batchable=batchable)
     except VerificationFailure:
         verdict = 1
     if "verifier" in trace:

@@ -19,6 +19,8 @@ static int be_malloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 16); retu
 static void be_free(void* p) { std::free(p); }
 static int be_h2d(void* d, const void* h, size_t n, be_stream) { std::memcpy(d, h, n); return 0; }
 static int be_d2h(void* h, const void* d, size_t n, be_stream) { std::memcpy(h, d, n); return 0; }
+static int be_d2d(void* d, const void* s, size_t n, be_stream) { std::memcpy(d, s, n); return 0; }
+static int be_os_random(void* p, size_t n) { FILE* f = std::fopen("/dev/urandom", "rb"); if (!f) return 1; size_t k = std::fread(p, 1, n, f); std::fclose(f); return k != n; }
 static int be_memset(void* d, int v, size_t n, be_stream) { std::memset(d, v, n); return 0; }
 static int be_sync(be_stream) { return 0; }
 static int be_check_launch() { return 0; }
@@ -70,14 +72,14 @@ static void be_launch_commit_compare(const Workspace& ws, const CmpPair* pairs, 
 }
 static u32 be_launch_rlc(const Workspace& ws, const RlcDesc* d, u32 ncterms, const RlcBuffers& rb, be_stream, be_event* = nullptr) {
     std::memset(rb.hist, 0, (size_t)rb.nwin * (rb.nb + 1) * 4);
-    for (u32 i = 0; i < ws.count; i++) rlc_scalars_job(ws, *d, rb, i);
+    for (u32 i = 0; i < rb.cnt; i++) rlc_scalars_job(ws, *d, rb, rb.lo + i);
     for (u32 t = 0; t < ncterms; t++) {
         u32 acc[9] = {0};
-        for (u32 i = 0; i < ws.count; i++) rlc_add288(acc, rb.cterm + ((size_t)t * ws.count + i) * 8);
+        for (u32 i = 0; i < rb.cnt; i++) rlc_add288(acc, rb.cterm + ((size_t)t * rb.cnt + i) * 8);
         sc r = rlc_reduce288(acc);
         for (int i = 0; i < 8; i++) rb.csum[8 * t + i] = r.v[i];
     }
-    for (u32 n = 0; n < rb.N; n++) rlc_digits_job(*d, rb, ws.count, n);
+    for (u32 n = 0; n < rb.N; n++) rlc_digits_job(*d, rb, n);
     for (u32 w = 0; w < rb.nwin; w++) rlc_scan_job(rb, w);
     for (u32 n = 0; n < rb.N; n++) rlc_scatter_job(rb, n);
     for (u32 w = 0; w < rb.nwin; w++) for (u32 b = 1; b <= rb.nb; b++) rlc_bucket_job(ws, *d, rb, w, b);

@@ -188,6 +188,11 @@ def test_issue_golden_shapes(coracle, name):
     v = iss.verify_issuance_batch(res)
     ov, _ = orc.verify_issuances(ik, np.ascontiguousarray(res.fields.transpose(1, 0, 2)))
     assert (v == ov).all() and (v[status == 1] == 1).all()
+    # item-major requests in, item-major issuances out (afx_issue_wire; 70 items over max_batch 64 = two passes)
+    wout, wst = iss.issue_wire(ik, np.ascontiguousarray(RequestBatch.from_request(ik, A, R).fields.transpose(1, 0, 2)))
+    good = status == 0
+    assert (wst == status).all() and (wout[good] == res.fields.transpose(1, 0, 2)[good]).all() and not wout[~good].any()
+    assert (iss.verify_wire(ik, wout, issuance=True) == ov).all()
 
 
 def test_issue_full_size_round_trip(readme4):
@@ -295,6 +300,8 @@ def test_show_golden_shapes(coracle, name):
     assert st[9] == 1 and not got[9].any() and not st[ok].any()
     assert (got[ok] == pres[ok]).all()
     assert got[0].tobytes().hex() == "".join(g["items"][0]["words"])
+    wgot, wst = user.show_wire(kinds, np.ascontiguousarray(fields.transpose(1, 0, 2)))      # afx_show_wire: item-major in and out
+    assert (wst == st).all() and (wgot == got).all()
     iss = Issuer(sp, ip, sk, device=0, max_batch=64)
     v = iss.verify_batch(res)
     ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(got))
@@ -439,3 +446,18 @@ def test_two_contexts_run_the_fused_ladders_concurrently(readme4):
 
     with ThreadPoolExecutor(max_workers=2) as pool:
         assert all(pool.map(worker, [101, 202]))
+
+
+def test_issuance_batchable_exact_and_rlc_on_gpu(coracle):
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_issuance_batchable
+    check_issuance_batchable(lambda sp, ip, sk, mb: Issuer(sp, ip, sk, device=0, max_batch=mb), coracle, count=700, max_batch=512)
+
+
+def test_rlc_bisection_on_gpu(coracle, monkeypatch):
+    """65,536 BatchableProof presentations with three bad items: the library's default 1,024-item leaves -- at most 3 x 1,024 items are
+    re-verified exactly and a few dozen small passes run; then 1 % bad items: bisection gives up, whole-chunk exact check."""
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_rlc_bisection
+    check_rlc_bisection(lambda sp, ip, sk, mb: Issuer(sp, ip, sk, device=0, max_batch=mb), coracle, count=65536, max_batch=65536, leaf=1024, n_bad=3,
+                        monkeypatch=monkeypatch)

@@ -126,6 +126,12 @@ def test_issue_stage_logic_matches_golden_and_oracle(emu, coracle, name):
     assert (st == status).all() and list(status) == [0, 0, 0, 1, 0]
     assert (res.fields.transpose(1, 0, 2)[:, n:] == out).all()
     assert list(iss.verify_issuance_batch(res)) == [0, 0, 0, 1, 0]
+    # item-major requests in, item-major issuances out (afx_issue_wire): the same bytes, ready for verify_wire
+    reqs = np.ascontiguousarray(RequestBatch.from_request(ik, A, R).fields.transpose(1, 0, 2))
+    wout, wst = iss.issue_wire(ik, reqs)
+    assert (wst == status).all() and (wout[[0, 1, 2, 4]] == res.fields.transpose(1, 0, 2)[[0, 1, 2, 4]]).all()
+    assert not wout[3].any()                                          # the malformed request: all-zero issuance, attributes included
+    assert list(iss.verify_wire(ik, wout, issuance=True)) == [0, 0, 0, 1, 0]
 
 
 @pytest.mark.parametrize("name", GOLDEN_SHAPES)
@@ -150,6 +156,8 @@ def test_show_stage_logic_matches_golden_and_oracle(emu, coracle, name):
     assert got[0].tobytes().hex() == "".join(g["items"][0]["words"])
     if st[3]:
         assert not got[3].any()
+    wgot, wst = user.show_wire(kinds, np.ascontiguousarray(fields.transpose(1, 0, 2)))      # item-major in and out (afx_show_wire)
+    assert (wst == st).all() and (wgot == got).all()
     iss = Issuer(sp, ip, sk, max_batch=8, _binding=emu)
     v = iss.verify_batch(res)
     ov, _ = orc.verify_presentations(kinds, np.ascontiguousarray(got))
@@ -524,3 +532,96 @@ def test_submit_refuses_a_shape_the_inflight_workspace_cannot_hold(emu, coracle)
     b = iss.submit(PresentationBatch.from_items(kinds, pres))            # idle: the workspace grows
     c = iss.submit(PresentationBatch.from_items(ik, issu), issuance=True)  # fits what the presentation sized
     assert not b.wait().any() and not c.wait().any()
+
+
+def issuance_to_batchable(issu, commitments):
+    """Compact issuances [count][2n+9][32] + the three commitments their proofs recompute [count][3][32] -> the BatchableProof layout
+    [count][2n+11][32]: attribute[n], t, U, V, commitments[3], responses[n+5]."""
+    n = (issu.shape[1] - 9) // 2
+    return np.ascontiguousarray(np.concatenate([issu[:, :n + 3], commitments, issu[:, n + 4:]], axis=1))
+
+
+def check_issuance_batchable(make_issuer, coracle, count, max_batch):
+    """BatchableProof issuances (issuance.rs:21-22's commented-out BatchVerifier): the exact per-constraint check and the random
+    linear combination agree with the Python restatement of zkp's verify_batchable -- honest items, corrupted commitment, response,
+    attribute, identity commitment, undecodable commitment."""
+    from aeonflux_b200 import PresentationBatch
+    from oracle.pyoracle import aeonflux as A, flat as F
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    _, _, issu = orc.synth(b"SSPE", [], b"iss-batchable", 0, count)
+    ik = bytes([0, 0, 2, 2])
+    ov, _, tr = orc.verify_issuances(ik, issu, trace=True)
+    assert not ov.any()
+    bi = issuance_to_batchable(issu, tr["commitments"])
+    iss = make_issuer(sp, ip, sk, max_batch)
+    assert bi.shape[1] == iss._b.L.afx_issuance_batchable_num_fields(4) == 19
+    v, dbg = iss.verify_issuance_batchable(PresentationBatch.from_items(ik, bi), debug=True)
+    assert not v.any()
+    assert (dbg["challenges"][0] == issu[:, 7]).all()                 # the derived challenge is the compact proof's
+    p0, e0 = iss.rlc_stats()
+    vr, fb = iss.verify_batchable_rlc(PresentationBatch.from_items(ik, bi), bytes(32), issuance=True)
+    assert not vr.any() and fb == 0
+    assert iss.rlc_stats() == (p0 + -(-count // max_batch), e0)      # one pass per chunk, nothing re-verified
+    bad = bi.copy()
+    bad[1, 7, 5] ^= 1          # commitment C_W
+    bad[2, 10, 0] ^= 1         # response w
+    bad[3, 0, 0] ^= 1          # a scalar attribute
+    bad[4, 8] = 0              # an identity commitment
+    bad[5, 9] = 0xff           # an undecodable commitment
+    sysp = A.SystemParameters.from_bytes(sp)
+    from oracle.pyoracle import ristretto as R
+    ipp = A.IssuerParameters(R.decompress(ip[:32]), R.decompress(ip[32:]))
+    expect = [F.verify_issuance_flat(sysp, ipp, ik, [bad[i, w].tobytes() for w in range(19)], batchable=True)[0] for i in range(min(count, 8))]
+    assert expect[:7] == [0, 1, 1, 1, 1, 1, 0]
+    full = np.zeros(count, np.uint8); full[1:6] = 1
+    assert (iss.verify_issuance_batchable(PresentationBatch.from_items(ik, bad)) == full).all()
+    vr, fb = iss.verify_batchable_rlc(PresentationBatch.from_items(ik, bad), bytes(32), issuance=True)
+    assert (vr == full).all() and fb >= 1
+    user = make_issuer(sp, ip, None, max_batch)                       # needs no secret key
+    assert (user.verify_batchable_rlc(PresentationBatch.from_items(ik, bad), bytes(range(32)), issuance=True)[0] == full).all()
+
+
+def test_issuance_batchable_exact_and_rlc(emu, coracle):
+    from aeonflux_b200 import Issuer
+    check_issuance_batchable(lambda sp, ip, sk, mb: Issuer(sp, ip, sk, max_batch=mb, _binding=emu), coracle, count=9, max_batch=7)
+
+
+def check_rlc_bisection(make_issuer, coracle, count, max_batch, leaf, n_bad, monkeypatch):
+    """A chunk whose combination does not vanish is bisected: with a few bad items only the leaves that hold them are re-verified
+    exactly, the verdicts are exact, and the number of passes / re-verified items stays far below the chunk."""
+    from aeonflux_b200 import PresentationBatch
+    from tests.common import to_batchable
+    monkeypatch.setenv("AFX_RLC_LEAF", str(leaf))
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, _ = orc.synth(b"SSPE", [0, 3], b"bisect", 0, min(count, 64), want_issuances=False)
+    ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+    bp = to_batchable(kinds, pres, tr["commitments"])
+    rng = np.random.default_rng(8)
+    items = bp[rng.integers(0, len(bp), count)].copy()
+    bad = np.sort(rng.choice(count, n_bad, replace=False))
+    for i in bad:
+        items[i, rng.integers(0, items.shape[1]), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+    expect = np.zeros(count, np.uint8); expect[bad] = 1
+    iss = make_issuer(sp, ip, sk, max_batch)
+    p0, e0 = iss.rlc_stats()
+    v, fb = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, items), bytes(32))
+    p1, e1 = iss.rlc_stats()
+    assert (v == expect).all()
+    chunks = -(-count // max_batch)
+    assert fb == len({int(i) // max_batch for i in bad})
+    assert 0 < e1 - e0 <= n_bad * leaf, (e1 - e0, n_bad, leaf)           # only the suspect leaves were re-verified
+    depth = int(np.ceil(np.log2(max_batch / leaf)))
+    assert chunks < p1 - p0 <= chunks + n_bad * 2 * (depth + 1), (p1 - p0, depth)
+    # many bad items: bisection gives up and the whole chunk is checked exactly -- same verdicts
+    for i in range(0, count, 3):
+        items[i, 1, 0] ^= 1
+        expect[i] = 1
+    v, fb = iss.verify_batchable_rlc(PresentationBatch.from_items(kinds, items), bytes(32))
+    assert (v == expect).all() and fb == chunks
+
+
+def test_rlc_bisection_on_emulation(emu, coracle, monkeypatch):
+    from aeonflux_b200 import Issuer
+    check_rlc_bisection(lambda sp, ip, sk, mb: Issuer(sp, ip, sk, max_batch=mb, _binding=emu), coracle, count=70, max_batch=64, leaf=4, n_bad=2, monkeypatch=monkeypatch)
