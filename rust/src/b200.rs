@@ -1,62 +1,21 @@
-//! FFI to `libaeonflux_b200.so` (include/aeonflux_b200.h) and a safe wrapper over byte slices.
+//! Safe wrappers over `libaeonflux_b200.so` (include/aeonflux_b200.h) for the batch entry points INTEGRATION.md adds beside
+//! `Issuer::verify`, `Issuer::issue` and `CredentialIssuance::verify`.
 //!
-//! Not compiled in this repository's image (no Rust toolchain); see rust/README.md.  Everything is expressed over the
-//! reference's own byte encodings: `SystemParameters::to_bytes()` (src/parameters.rs:155-184), the 64 bytes `C_W || I`
-//! (src/issuer.rs:155,163), `amacs::SecretKey::to_bytes()` (src/amacs.rs:110-125), canonical scalars and compressed points.
+//! NEVER COMPILED in this repository: its build image has no Rust toolchain (rust/README.md).  The raw FFI -- extern block,
+//! #[repr(C)] descriptors, constants -- is `ffi.rs`, GENERATED from the header by tools/gen_rust_ffi.py (a CPU test regenerates it
+//! and compares, so it cannot drift); this file is hand-written and review-sized.  Everything is expressed over the reference's own
+//! byte encodings: `SystemParameters::to_bytes()` (src/parameters.rs:155-184), the 64 bytes `C_W || I` (src/issuer.rs:155,163),
+//! `amacs::SecretKey::to_bytes()` (src/amacs.rs:110-125), canonical scalars and compressed points.
 
-use std::os::raw::{c_char, c_int};
+use std::os::raw::c_int;
 
-#[repr(C)]
-pub struct afx_ctx {
-    _private: [u8; 0],
-}
+#[path = "ffi.rs"]
+mod ffi;
+pub use ffi::*;
 
-/// `afx_presentation_batch`, `afx_issuance_batch`, `afx_request_batch` and `afx_show_batch` share this layout.
-#[repr(C)]
-pub struct afx_batch {
-    pub n_attrs: u16,
-    pub kinds: *const u8,
-    pub count: usize,
-    pub fields: *const *const u8,
-    pub n_fields: usize,
-}
-
-/// `afx_issuance_out` / `afx_presentation_out`.
-#[repr(C)]
-pub struct afx_out {
-    pub fields: *const *mut u8,
-    pub n_fields: usize,
-}
-
-#[repr(C)]
-pub struct afx_debug_dump {
-    pub z: *mut u8,
-    pub commitments: *mut u8,
-    pub challenges: *mut u8,
-    pub status: *mut u32,
-}
-
-extern "C" {
-    pub fn afx_ctx_create(sysparams: *const u8, sysparams_len: usize, issuer_pub: *const u8, secret: *const u8, secret_len: usize,
-                          device: c_int, max_batch: usize, out: *mut *mut afx_ctx) -> c_int;
-    pub fn afx_ctx_destroy(ctx: *mut afx_ctx);
-    pub fn afx_presentation_num_fields(n_attrs: u16, kinds: *const u8) -> usize;
-    pub fn afx_request_num_fields(n_attrs: u16) -> usize;
-    pub fn afx_show_num_fields(n_attrs: u16, kinds: *const u8) -> usize;
-    pub fn afx_verify_presentations(ctx: *mut afx_ctx, batch: *const afx_batch, verdicts: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
-    pub fn afx_verify_presentations_wire(ctx: *mut afx_ctx, n_attrs: u16, kinds: *const u8, count: usize, items: *const u8,
-                                         verdicts: *mut u8) -> c_int;
-    pub fn afx_verify_issuances(ctx: *mut afx_ctx, batch: *const afx_batch, verdicts: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
-    pub fn afx_verify_issuances_wire(ctx: *mut afx_ctx, n_attrs: u16, kinds: *const u8, count: usize, items: *const u8,
-                                     verdicts: *mut u8) -> c_int;
-    pub fn afx_issue(ctx: *mut afx_ctx, batch: *const afx_batch, out: *const afx_out, status: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
-    pub fn afx_show(ctx: *mut afx_ctx, batch: *const afx_batch, out: *const afx_out, status: *mut u8, dbg: *mut afx_debug_dump) -> c_int;
-    pub fn afx_verify_presentations_submit(ctx: *mut afx_ctx, batch: *const afx_batch, verdicts: *mut u8, ticket: *mut u64) -> c_int;
-    pub fn afx_wait(ctx: *mut afx_ctx, ticket: u64) -> c_int;
-    pub fn afx_host_alloc(out: *mut *mut std::os::raw::c_void, bytes: usize) -> c_int;
-    pub fn afx_host_free(p: *mut std::os::raw::c_void);
-    pub fn afx_strerror(code: c_int) -> *const c_char;
-}
+/// `afx_presentation_batch`, `afx_issuance_batch`, `afx_request_batch` and `afx_show_batch` share one layout.
+type afx_batch = afx_presentation_batch;
+type afx_out = afx_issuance_out;
 
 /// A byte buffer in page-locked host memory (`afx_host_alloc`).  Build the struct-of-arrays fields of a batch in these:
 /// the library's host-to-device copies then run asynchronously at the full bus rate instead of being staged by the driver.
@@ -226,5 +185,63 @@ impl Drop for B200Context {
     /// Zeroizes the device and host copies of the secret key (src/amacs.rs:64-82 semantics) and frees the context.
     fn drop(&mut self) {
         unsafe { afx_ctx_destroy(self.ctx) }
+    }
+}
+
+
+/// Several B200s behind one handle (`afx_multi_*`): the library replicates the issuer context on every listed device, keeps one
+/// host thread per device, cuts a batch into contiguous item slices (device k of G takes `[k*N/G, (k+1)*N/G)`) and lets every
+/// device write its slice of the verdict array.  This is what `Issuer::verify_batch` binds when the box has more than one GPU.
+pub struct B200Multi {
+    m: *mut afx_multi,
+}
+
+unsafe impl Send for B200Multi {}
+
+impl B200Multi {
+    pub fn new(system_parameters: &[u8], issuer_parameters: &[u8; 64], secret_key: Option<&[u8]>, devices: &[i32], max_batch_per_device: usize)
+        -> Result<B200Multi, B200Error>
+    {
+        let mut m: *mut afx_multi = std::ptr::null_mut();
+        let (sk, sk_len) = match secret_key { Some(s) => (s.as_ptr(), s.len()), None => (std::ptr::null(), 0) };
+        let devs: Vec<c_int> = devices.iter().map(|d| *d as c_int).collect();
+        let rc = unsafe {
+            afx_multi_create(system_parameters.as_ptr(), system_parameters.len(), issuer_parameters.as_ptr(), sk, sk_len,
+                             devs.as_ptr(), devs.len() as c_int, max_batch_per_device, &mut m)
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(B200Multi { m })
+    }
+
+    /// Batch `Issuer::verify` over item-major wire bytes, sharded over the devices.
+    pub fn verify_presentations_wire(&self, kinds: &[u8], items: &[u8]) -> Result<Vec<u8>, B200Error> {
+        let n_fields = unsafe { afx_presentation_num_fields(kinds.len() as u16, kinds.as_ptr()) };
+        if n_fields == 0 || items.len() % (n_fields * 32) != 0 { return Err(B200Error(-1)); }
+        let count = items.len() / (n_fields * 32);
+        let mut verdicts = vec![0u8; count];
+        let rc = unsafe {
+            afx_multi_verify_presentations_wire(self.m, kinds.len() as u16, kinds.as_ptr(), count, items.as_ptr(), verdicts.as_mut_ptr())
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(verdicts)
+    }
+
+    /// Batch `CredentialIssuance::verify` over item-major wire bytes (`attribute[n], t, U, V, challenge, responses[n+5]` per item).
+    pub fn verify_issuances_wire(&self, kinds: &[u8], items: &[u8]) -> Result<Vec<u8>, B200Error> {
+        let n_fields = 2 * kinds.len() + 9;
+        if items.len() % (n_fields * 32) != 0 { return Err(B200Error(-1)); }
+        let count = items.len() / (n_fields * 32);
+        let mut verdicts = vec![0u8; count];
+        let rc = unsafe {
+            afx_multi_verify_issuances_wire(self.m, kinds.len() as u16, kinds.as_ptr(), count, items.as_ptr(), verdicts.as_mut_ptr())
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(verdicts)
+    }
+}
+
+impl Drop for B200Multi {
+    fn drop(&mut self) {
+        unsafe { afx_multi_destroy(self.m) }
     }
 }

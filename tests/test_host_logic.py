@@ -32,6 +32,19 @@ def test_cabi_library_exports_declared_symbols():
     assert "sm_100a" in out
 
 
+def test_rust_ffi_is_generated_from_the_header():
+    """rust/src/ffi.rs (the extern block of the Rust shim, which cannot be compiled here) is exactly what tools/gen_rust_ffi.py makes
+    of include/aeonflux_b200.h, and declares every exported function."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    text = g.generate()
+    assert open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read() == text, "run python tools/gen_rust_ffi.py"
+    from aeonflux_b200._binding import Binding
+    for name in Binding.SYMBOLS:
+        assert ("pub fn %s(" % name) in text, name
+
+
 def test_product_has_no_cpu_fallback():
     """The package never imports the oracle or the emulation harness, and refuses to run without the CUDA build."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "aeonflux_b200")):

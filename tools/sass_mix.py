@@ -1,54 +1,53 @@
 #!/usr/bin/env python
-"""Executed-instruction mix of the kernels in an `ncu --page source --csv --print-source sass` dump: per kernel, executed warp
-instructions by opcode (top 25) and the share of local-memory instructions (LDL/STL), with the hottest of those by address -- the
-evidence for "no spill traffic inside the window body".  Usage: python tools/sass_mix.py src.csv"""
+"""Executed-instruction report of ONE kernel from an `ncu -i X.ncu-rep --page source --csv --print-source sass` dump (optionally .gz):
+executed warp instructions by opcode, and every local-memory instruction (LDL/STL = register spills) with how often it executes per
+warp -- the evidence for "no spill traffic inside the multiply / window bodies".
+    python tools/sass_mix.py gpurun_out/src_k_ladders.csv.gz > profiles/rNN_sass_k_ladders.txt"""
 import collections
 import csv
+import gzip
+import io
 import sys
 
 
+def opcode(src):
+    toks = [t for t in src.split() if not t.startswith("@")]
+    return toks[0].rstrip(";") if toks else "?"
+
+
 def main():
-    rows = list(csv.reader(open(sys.argv[1], newline="")))
-    kernel, hdr = None, None
-    per = collections.OrderedDict()
-    for r in rows:
-        if not r:
-            continue
-        if len(r) == 1 or (r[0].startswith("Kernel") and len(r) <= 3):
-            kernel = r[-1]; hdr = None
-            continue
-        if hdr is None and ("Source" in r or "# Source" in r or any(c.strip() in ("Source", "SASS") for c in r)):
-            hdr = [c.strip() for c in r]
-            continue
-        if hdr is None:
-            continue
-        d = dict(zip(hdr, r))
-        src = d.get("Source") or d.get("SASS") or ""
-        ex = d.get("Warp Instructions Executed") or d.get("Instructions Executed") or d.get("# Instructions Executed") or "0"
-        try:
-            n = int(float(ex.replace(",", "")))
-        except ValueError:
-            continue
-        toks = src.replace("@P", " @P").split()
-        toks = [t for t in toks if not t.startswith("@") and not t.startswith("/*")]
-        if not toks:
-            continue
-        op = toks[0].rstrip(";")
-        k = per.setdefault(kernel or "?", {"ops": collections.Counter(), "local": []})
-        k["ops"][op] += n
-        if op.startswith(("LDL", "STL")):
-            k["local"].append((n, d.get("Address", ""), src.strip()))
-    for name, k in per.items():
-        tot = sum(k["ops"].values())
-        if not tot:
-            continue
-        print("== %s: %d executed warp instructions" % (name, tot))
-        for op, n in k["ops"].most_common(25):
-            print("  %-22s %14d  %5.2f %%" % (op, n, 100.0 * n / tot))
-        loc = sum(n for n, _, _ in k["local"])
-        print("  local-memory (LDL/STL) executed: %d = %.3f %% of all" % (loc, 100.0 * loc / tot))
-        for n, a, srcl in sorted(k["local"], reverse=True)[:8]:
-            print("    %12d  %s  %s" % (n, a, srcl))
+    path = sys.argv[1]
+    f = io.TextIOWrapper(gzip.open(path)) if path.endswith(".gz") else open(path, newline="")
+    rows = list(csv.reader(f))
+    name = rows[0][1] if rows and rows[0] and rows[0][0] == "Kernel Name" else "?"
+    hdr = rows[1]
+    ia, isrc, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed")
+    ins = [(int(r[ia], 16), r[isrc].strip(), int(r[iex])) for r in rows[2:] if len(r) > iex and r[ia].startswith("0x")]
+    warps = ins[0][2]                      # the first instruction runs once per warp
+    tot = sum(n for _, _, n in ins)
+    print("kernel: %s" % name)
+    print("static instructions: %d   warps launched: %d   executed warp instructions: %d (%.0f per warp on average)" % (len(ins), warps, tot, tot / warps))
+    ops, static = collections.Counter(), collections.Counter()
+    for _, s, n in ins:
+        ops[opcode(s)] += n
+        static[opcode(s)] += 1
+    print("\nopcode                 executed warp instr     share   static count")
+    for op, n in ops.most_common(30):
+        print("  %-20s %18d  %6.2f %%  %8d" % (op, n, 100.0 * n / tot, static[op]))
+    loc = [(a, s, n) for a, s, n in ins if opcode(s).startswith(("LDL", "STL"))]
+    le = sum(n for _, _, n in loc)
+    print("\nlocal-memory instructions (LDL/STL): %d static, %d executed = %.3f %% of all executed instructions" % (len(loc), le, 100.0 * le / tot))
+    hist = collections.Counter()
+    for _, _, n in loc:
+        x = n / warps
+        hist["never" if n == 0 else "< 1" if x < 1 else "1 .. 8" if x < 8 else "8 .. 64" if x < 64 else ">= 64"] += 1
+    print("executions per launched warp -> number of LDL/STL instructions:", dict(hist))
+    hottest = max(n for _, _, n in ins)
+    print("for scale: the hottest instruction of the kernel executes %.0f times per launched warp; IMAD.WIDE instructions average %.0f"
+          % (hottest / warps, sum(n for _, s, n in ins if opcode(s).startswith("IMAD.WIDE")) / max(1, sum(1 for _, s, _ in ins if opcode(s).startswith("IMAD.WIDE"))) / warps))
+    print("the local-memory instructions that execute most often:")
+    for a, s, n in sorted(loc, key=lambda t: -t[2])[:12]:
+        print("  %8.1f per warp   0x%x   %s" % (n / warps, a, s))
 
 
 if __name__ == "__main__":
