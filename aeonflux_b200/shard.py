@@ -57,12 +57,15 @@ class ShardedIssuer:
             except ImportError:
                 pass
         self.rank, self.world = rank, world
+        self.gather_seconds = 0.0
 
     # -- the only communication on the path: the verdict bitmap ------------------------------------------------------
     def _gather_bitmaps(self, local_bits: np.ndarray, total: int) -> np.ndarray:
         if self.world == 1:
             return unpack_bitmap(local_bits, total)
+        import time
         import torch
+        t0 = time.perf_counter()
         import torch.distributed as dist
         width = (-(-total // self.world) + 7) // 8 + 1          # bytes of the largest slice's bitmap
         dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
@@ -76,6 +79,7 @@ class ShardedIssuer:
         for r in range(self.world):
             lo, hi = slice_bounds(total, r, self.world)
             out[lo:hi] = unpack_bitmap(parts[r], hi - lo)
+        self.gather_seconds += time.perf_counter() - t0      # includes waiting for the slowest rank
         return out
 
     def local_slice(self, batch: PresentationBatch) -> PresentationBatch:

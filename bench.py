@@ -697,12 +697,14 @@ def main():
     for _ in range(2):
         assert (sharded.verify_wire(kinds, wire_global.numpy()) == expect).all(), "sharded verdicts differ from the expected set"
     barrier()
+    sharded.gather_seconds = 0.0
     with clocks.window():
         t0 = time.perf_counter()
         for _ in range(args.steps):
             v = sharded.verify_wire(kinds, wire_global.numpy())
         barrier()
         e2e_s = time.perf_counter() - t0
+    gather_ms = 1e3 * sharded.gather_seconds / args.steps
     assert (v == expect).all()
     # also timed, per rank on its own slice (no gather): the struct-of-arrays entry and the streamed submit / wait form
     host = torch.empty((WORDS, B, 32), dtype=torch.uint8).pin_memory()
@@ -801,6 +803,7 @@ def main():
                            "(H2D of the slice, kernels, D2H of its verdicts) -> accept/reject bitmap all-gathered%s; every rank returns all %d verdicts; %d corrupted items, verdict vector checked"
                            % (world, " over NCCL" if world > 1 else " (world 1: no collective)", world * B, len(bad)),
                     "collective_bytes_per_step": bitmap_bytes * world * world if world > 1 else 0,
+                    "gather_ms_per_step_rank0": gather_ms, "gather_note": "bitmap pack + all-gather + unpack on rank 0, including the wait for the slowest rank of the step",
                     "soa_api_value": total_items / (e2e_soa_ms_max * 1e-3),
                     "streamed_value": total_items / (e2e_stream_ms_max * 1e-3),
                     "streamed_api": "per rank, no gather: afx_verify_presentations_wire_submit / afx_wait, two submissions in flight (same per-step H2D and D2H bytes; "
