@@ -34,7 +34,7 @@ class Binding:
                "afx_multi_create", "afx_multi_destroy", "afx_multi_num_devices", "afx_multi_ctx", "afx_multi_verify_presentations",
                "afx_multi_verify_presentations_wire", "afx_multi_verify_issuances", "afx_multi_verify_issuances_wire", "afx_multi_issue",
                "afx_verify_presentations_wire_submit", "afx_verify_issuances_wire_submit", "afx_stream_create", "afx_stream_destroy",
-               "afx_stream_add_shape", "afx_stream_push", "afx_stream_flush", "afx_stream_buckets_submitted",
+               "afx_stream_add_shape", "afx_stream_push", "afx_stream_flush", "afx_stream_buckets_submitted", "afx_stream_times",
                "afx_issue_wire", "afx_show_wire", "afx_issuance_batchable_num_fields", "afx_verify_issuances_batchable", "afx_verify_issuances_batchable_rlc", "afx_get_rlc_stats"]
 
     def __init__(self, cdll):
@@ -124,6 +124,8 @@ class Binding:
         L.afx_stream_push.argtypes = [vp, vp, vp, vp, sz, vp]
         L.afx_stream_flush.restype = ctypes.c_int
         L.afx_stream_flush.argtypes = [vp]
+        L.afx_stream_times.restype = ctypes.c_int
+        L.afx_stream_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.afx_stream_buckets_submitted.restype = ctypes.c_uint64
         L.afx_stream_buckets_submitted.argtypes = [vp]
         L.afx_multi_create.restype = ctypes.c_int

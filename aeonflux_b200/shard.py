@@ -268,6 +268,13 @@ class MixedStream:
         self._b.check(self._b.L.afx_stream_flush(self._h))
         self._keep = [k for k in self._keep if not isinstance(k, tuple)]
 
+    def times(self):
+        """Cumulative host seconds of the driving thread: (copying records into buckets, enqueueing submissions, blocked on the device)."""
+        import ctypes
+        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        self._b.check(self._b.L.afx_stream_times(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
     @property
     def buckets_submitted(self):
         return int(self._b.L.afx_stream_buckets_submitted(self._h))

@@ -530,6 +530,7 @@ def stream_config5(torch, dist, sharded4, rank, world, local, total, stream, cor
         dist.barrier()
     torch.cuda.synchronize()
     b0 = ms.buckets_submitted
+    tm0 = ms.times()
     t0 = time.perf_counter()
     local_v = np.zeros(mine, np.uint8)
     ms.push(blob, offsets, order, local_v)
@@ -538,6 +539,7 @@ def stream_config5(torch, dist, sharded4, rank, world, local, total, stream, cor
     allv = sharded4._gather_bitmaps(pack_bitmap(local_v), total) if world > 1 else local_v
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    tm1 = ms.times()
     mism = int((local_v != expect).sum())
     assert mism == 0, "%d verdict mismatches in the config-5 stream" % mism
     t = torch.tensor([wall, float(mism), float(expect.sum())], dtype=torch.float64, device="cuda")
@@ -550,7 +552,9 @@ def stream_config5(torch, dist, sharded4, rank, world, local, total, stream, cor
                        "incl. byte-31 bit flips), rank r pushing stream slice r through afx_stream_* (BASELINE configs[4])" % total,
            "value": total / float(t[0].item()), "unit": "presentations/s", "wall_s": float(t[0].item()), "n_gpus": world, "items": total, "rejected": int(tot[2].item()),
            "mismatches": int(tot[1].item()), "buckets_per_rank": ms.buckets_submitted - b0, "bucket_items": chunk,
-           "h2d_bytes": int(n4 * WORDS * 32 + n16 * WORDS_S16 * 32), "timing": "wall clock: push (bucketing into page-locked double buffers, asynchronous wire submits) + flush + bitmap all-gather, max over ranks; "
+           "h2d_bytes": int(n4 * WORDS * 32 + n16 * WORDS_S16 * 32),
+           "host_thread_s_rank0": {"bucketing_memcpy": tm1[0] - tm0[0], "enqueue": tm1[1] - tm0[1], "blocked_on_device": tm1[2] - tm0[2]},
+           "timing": "wall clock: push (bucketing into page-locked double buffers, asynchronous wire submits) + flush + bitmap all-gather, max over ranks; "
                                                                              "one warm-up bucket per shape untimed",
            "input": "every item distinct, issued and shown on the rank's device (%.1f s, untimed)" % t_gen}
     if with_cpu and rank == 0:

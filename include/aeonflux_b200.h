@@ -284,6 +284,8 @@ int afx_stream_push(afx_stream* stream, const uint8_t* records, const uint64_t* 
                     uint8_t* verdicts);
 int afx_stream_flush(afx_stream* stream);
 uint64_t afx_stream_buckets_submitted(const afx_stream* stream);
+/* Cumulative host time of the driving thread: copying records into buckets, enqueueing submissions, blocked waiting for the device. */
+int afx_stream_times(const afx_stream* stream, double* fill_s, double* submit_s, double* wait_s);
 
 /* Primitive self-test (parity hooks for the field / group / scalar code, independent of the protocol flows).  `in` is
  * item-major, `out` is [count][32], ok[i] = 1 unless an input encoding was rejected.
