@@ -534,12 +534,20 @@ def stream_config5(torch, dist, sharded4, rank, world, local, total, stream, cor
     t0 = time.perf_counter()
     local_v = np.zeros(mine, np.uint8)
     ms.push(blob, offsets, order, local_v)
+    t_push = time.perf_counter()
     ms.flush()
+    t_flush = time.perf_counter()
     from aeonflux_b200.shard import pack_bitmap
     allv = sharded4._gather_bitmaps(pack_bitmap(local_v), total) if world > 1 else local_v
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     tm1 = ms.times()
+    mine_split = {"rank": rank, "push_s": t_push - t0, "flush_s": t_flush - t_push, "gather_s": wall - (t_flush - t0), "bucketing_memcpy_s": tm1[0] - tm0[0],
+                  "enqueue_s": tm1[1] - tm0[1], "blocked_on_device_s": tm1[2] - tm0[2]}
+    splits = [mine_split]
+    if world > 1:
+        splits = [None] * world
+        dist.all_gather_object(splits, mine_split)
     mism = int((local_v != expect).sum())
     assert mism == 0, "%d verdict mismatches in the config-5 stream" % mism
     t = torch.tensor([wall, float(mism), float(expect.sum())], dtype=torch.float64, device="cuda")
@@ -553,7 +561,7 @@ def stream_config5(torch, dist, sharded4, rank, world, local, total, stream, cor
            "value": total / float(t[0].item()), "unit": "presentations/s", "wall_s": float(t[0].item()), "n_gpus": world, "items": total, "rejected": int(tot[2].item()),
            "mismatches": int(tot[1].item()), "buckets_per_rank": ms.buckets_submitted - b0, "bucket_items": chunk,
            "h2d_bytes": int(n4 * WORDS * 32 + n16 * WORDS_S16 * 32),
-           "host_thread_s_rank0": {"bucketing_memcpy": tm1[0] - tm0[0], "enqueue": tm1[1] - tm0[1], "blocked_on_device": tm1[2] - tm0[2]},
+           "per_rank_seconds": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in sp.items()} for sp in splits],
            "timing": "wall clock: push (bucketing into page-locked double buffers, asynchronous wire submits) + flush + bitmap all-gather, max over ranks; "
                                                                              "one warm-up bucket per shape untimed",
            "input": "every item distinct, issued and shown on the rank's device (%.1f s, untimed)" % t_gen}
