@@ -30,7 +30,7 @@ class AfxError(RuntimeError):
 class Binding:
     SYMBOLS = ["afx_ctx_create", "afx_ctx_destroy", "afx_presentation_num_fields", "afx_presentation_num_commitments",
                "afx_presentation_num_proofs", "afx_verify_presentations", "afx_verify_presentations_device", "afx_verify_issuances",
-               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_host_alloc", "afx_host_free", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_get_rlc_bucket_time", "afx_strerror", "afx_version",
+               "afx_verify_issuances_device", "afx_verify_presentations_submit", "afx_verify_issuances_submit", "afx_wait", "afx_host_alloc", "afx_host_free", "afx_batchable_num_fields", "afx_verify_presentations_batchable", "afx_verify_presentations_batchable_rlc", "afx_verify_presentations_wire", "afx_verify_issuances_wire", "afx_request_num_fields", "afx_issue", "afx_issue_device", "afx_show_num_fields", "afx_show", "afx_show_device", "afx_selftest_primitive", "afx_launch_count", "afx_ctx_device", "afx_bind_thread_to_device", "afx_set_stage_timing", "afx_get_stage_times", "afx_get_rlc_bucket_time", "afx_strerror", "afx_version",
                "afx_multi_create", "afx_multi_destroy", "afx_multi_num_devices", "afx_multi_ctx", "afx_multi_verify_presentations",
                "afx_multi_verify_presentations_wire", "afx_multi_verify_issuances", "afx_multi_verify_issuances_wire", "afx_multi_issue",
                "afx_verify_presentations_wire_submit", "afx_verify_issuances_wire_submit", "afx_stream_create", "afx_stream_destroy",
@@ -108,6 +108,8 @@ class Binding:
         L.afx_get_rlc_bucket_time.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
         L.afx_ctx_device.restype = ctypes.c_int
         L.afx_ctx_device.argtypes = [vp]
+        L.afx_bind_thread_to_device.restype = ctypes.c_int
+        L.afx_bind_thread_to_device.argtypes = [ctypes.c_int]
         L.afx_strerror.restype = ctypes.c_char_p
         L.afx_strerror.argtypes = [ctypes.c_int]
         L.afx_version.restype = ctypes.c_char_p

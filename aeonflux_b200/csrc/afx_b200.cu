@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <sched.h>
 #include <sys/random.h>
 
 #include "engine.cuh"
@@ -302,6 +303,35 @@ static int be_check_launch() {
     return 0;
 }
 static int be_os_random(void* p, size_t n) { return getrandom(p, n, 0) != (ssize_t)n; }
+// Pin the calling thread to the CPUs of the NUMA node the device hangs off (sysfs local_cpulist of its PCI function), so that the
+// page-locked staging it allocates next is node-local and its copies do not cross the socket interconnect.  Best effort: returns
+// non-zero and changes nothing when the topology cannot be read.
+static int be_bind_thread_to_device(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return 1;
+    for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return 1;
+    char list[4096] = {0};
+    size_t got = std::fread(list, 1, sizeof list - 1, f);
+    std::fclose(f);
+    if (!got) return 1;
+    cpu_set_t set; CPU_ZERO(&set);
+    int any = 0;
+    for (char* p = list; *p;) {
+        char* end;
+        long a = std::strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        if (*end == '-') { p = end + 1; b = std::strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, &set); any = 1; }
+        p = (*end == ',') ? end + 1 : end;
+        if (*end != ',' ) break;
+    }
+    if (!any) return 1;
+    return sched_setaffinity(0, sizeof set, &set) != 0;
+}
 typedef cudaEvent_t be_event;
 static void be_event_create(be_event* e) { cudaEventCreate(e); }
 static void be_event_destroy(be_event e) { cudaEventDestroy(e); }

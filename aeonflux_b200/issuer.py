@@ -97,6 +97,15 @@ class RequestBatch(PresentationBatch):
         return RequestBatch(kinds, np.ascontiguousarray(items.transpose(1, 0, 2)))
 
 
+def bind_thread_to_device(device: int, _binding=None) -> bool:
+    """Pin the calling thread (and with it the page-locked staging it allocates next) to the CPUs local to `device`
+    (afx_bind_thread_to_device).  For a one-process-per-GPU program: call it first.  Returns False if the topology is unreadable."""
+    if _binding is None:
+        from ._lib import load
+        _binding = load()
+    return _binding.L.afx_bind_thread_to_device(int(device)) == 0
+
+
 class Issuer:
     """An anonymous credential issuer/verifier bound to one B200 (issuer.rs:61-65)."""
 

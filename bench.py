@@ -268,15 +268,30 @@ def corrupt_items(items, kinds, idx, rng):
             items[i, rng.integers(0, items.shape[1]), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
 
 
+ALL_CPUS = os.sched_getaffinity(0)
+
+
+class all_cores:
+    """The GPU ranks pin their thread to the CPUs next to their device (afx_bind_thread_to_device); a CPU leg runs on every core."""
+
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, ALL_CPUS)
+
+    def __exit__(self, *a):
+        os.sched_setaffinity(0, self.saved)
+
+
 def cpu_leg(sp, ip, sk, kinds, items, threads):
     """The restated reference CPU path (oracle/c, reference schedule) on `items` with `threads` host threads."""
     from oracle import coracle as C
     C.build()
     orc = C.Issuer(sp, ip, sk)
     sub = np.ascontiguousarray(items)
-    t0 = time.perf_counter()
-    verdicts, _ = orc.verify_presentations(kinds, sub, threads=threads)
-    wall = time.perf_counter() - t0
+    with all_cores():
+        t0 = time.perf_counter()
+        verdicts, _ = orc.verify_presentations(kinds, sub, threads=threads)
+        wall = time.perf_counter() - t0
     return verdicts, len(sub) / wall, wall
 
 
@@ -378,9 +393,10 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     sample = min(B, cores * 1024)
     attrs_s = np.ascontiguousarray(rq[:4, :sample].transpose(1, 0, 2))
     rnd_s = np.ascontiguousarray(rq[4:, :sample].transpose(1, 0, 2)).reshape(sample, n + 7, 64)
-    t0 = time.perf_counter()
-    oout, ostatus, _ = orc.issue(kinds, attrs_s, rnd_s, threads=cores)
-    cpu_wall = time.perf_counter() - t0
+    with all_cores():
+        t0 = time.perf_counter()
+        oout, ostatus, _ = orc.issue(kinds, attrs_s, rnd_s, threads=cores)
+        cpu_wall = time.perf_counter() - t0
     assert (issued.fields.transpose(1, 0, 2)[:sample, 4:] == oout).all(), "issuances differ from the CPU oracle's given the same rng bytes"
     out["issue_4attr"] = {"workload": "batch Issuer::issue (Amac::tag + ProofOfIssuance::prove) of %d revealed 4-attribute requests (BASELINE configs[2])" % B,
                           "value": B / (ms * 1e-3), "unit": "issuances/s", "ms_per_step": ms,
@@ -402,9 +418,10 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
     wire.numpy()[:] = issued.fields.transpose(1, 0, 2)
     e2e_s, v = time_wall(lambda: issuer4.verify_wire(kinds, wire.numpy(), issuance=True), steps)
     assert not v.any()
-    t0 = time.perf_counter()
-    ov, _ = orc.verify_issuances(kinds, np.ascontiguousarray(wire.numpy()[:sample]), threads=cores)
-    cpu_wall = time.perf_counter() - t0
+    with all_cores():
+        t0 = time.perf_counter()
+        ov, _ = orc.verify_issuances(kinds, np.ascontiguousarray(wire.numpy()[:sample]), threads=cores)
+        cpu_wall = time.perf_counter() - t0
     assert not ov.any()
     survey_imad = 2.158e6          # SURVEY 8d table, issuance-verify n = 4 [PS,PS,PP,EP]
     out["verify_issuance_4attr"] = {"workload": "batch CredentialIssuance::verify of the %d issuances above (BASELINE configs[2])" % B,
@@ -637,6 +654,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    from aeonflux_b200.issuer import bind_thread_to_device
+    numa_bound = bind_thread_to_device(local)          # before any pinned allocation: node-local staging for this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -808,7 +827,7 @@ def main():
     line = {"metric": "presentations_verified_per_sec", "value": value, "unit": "presentations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE carry chains)",
             "data": "synthetic", "config": CONFIG,
-            "clocks": clk, "gpu_launches": launches,
+            "clocks": clk, "gpu_launches": launches, "numa_bound": bool(numa_bound),
             "e2e": {"value": e2e_value, "unit": "presentations/s", "h2d_bytes_per_step": world * B * WORDS * 32, "d2h_bytes_per_step": world * (B + bitmap_bytes * world),
                     "ms_per_step": e2e_ms_max / args.steps,
                     "api": "ShardedIssuer.verify_wire on ONE global batch of %d x 65,536 items in pinned host memory: contiguous slice per rank -> afx_verify_presentations_wire "

@@ -319,6 +319,13 @@ int afx_get_rlc_bucket_time(afx_ctx* ctx, float* ms, uint64_t* inputs, uint32_t*
  * stream it passed; this returns the ordinal of the CUDA device the context lives on. */
 int afx_ctx_device(const afx_ctx* ctx);
 
+/* NUMA placement for the thread that drives a device (optional, best effort).  Pins the CALLING thread to the CPUs local to the
+ * device's PCI function (sysfs local_cpulist), so that page-locked staging it allocates afterwards is node-local and its copies do
+ * not cross the socket interconnect: call it before afx_ctx_create / afx_host_alloc in a one-process-per-GPU or one-thread-per-GPU
+ * program (measured on an 8 x B200 box: the config-5 stream of the four far-socket ranks ran 9 % slower without it).  The
+ * library's own device threads (afx_multi_*) do this themselves.  AFX_ERR_ARG when the topology cannot be read (nothing changes). */
+int afx_bind_thread_to_device(int device);
+
 const char* afx_strerror(int code);
 const char* afx_version(void);
 
