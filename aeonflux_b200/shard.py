@@ -224,7 +224,7 @@ class MultiGpuIssuer:
 
 class MixedStream:
     """Streamed verification of mixed shapes through the library's stream object (afx_stream_*, BASELINE configs[4]): records of
-    several shapes arrive interleaved; the library buckets them by shape into page-locked double buffers and submits every full
+    several shapes arrive interleaved; the library buckets them by shape into page-locked buckets (three per shape: one filling, two in flight) and submits every full
     bucket asynchronously, so bucketing, copies and kernels overlap.  Shapes of different attribute counts belong to different
     issuers: register each with the `Issuer` that verifies it."""
 

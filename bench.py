@@ -774,6 +774,25 @@ def main():
     sm_max = clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     imad_peak = 148 * 64 * sm_max * 1e6                       # IMAD issue slots/s at max clock (measured 18.52e12 by tools/microbench)
 
+    # diagnostic: host-to-device bandwidth of every rank with all ranks copying at once (256 MiB from page-locked memory, best of 3)
+    hb = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    db = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    best = 1e9
+    for _ in range(3):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); db.copy_(hb, non_blocking=True); e1.record(stream)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    h2d = torch.tensor([(256 << 20) / (best * 1e-3) / 1e9, dev_ms / args.steps], dtype=torch.float64, device="cuda")
+    per_rank = [torch.empty_like(h2d) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, h2d)
+    else:
+        per_rank = [h2d]
+    per_rank_diag = {"h2d_GBps_all_ranks_copying": [round(float(x[0]), 1) for x in per_rank], "device_ms_per_step": [round(float(x[1]), 2) for x in per_rank]}
+    del hb, db
+
     secondary = {}
     if world == 1 and not args.no_secondary:
         secondary = secondary_measurements(torch, issuer, honest_local, local, stream, flush, B, min(args.steps, 3), imad_peak, cores)
@@ -827,7 +846,7 @@ def main():
     line = {"metric": "presentations_verified_per_sec", "value": value, "unit": "presentations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE carry chains)",
             "data": "synthetic", "config": CONFIG,
-            "clocks": clk, "gpu_launches": launches, "numa_bound": bool(numa_bound),
+            "clocks": clk, "gpu_launches": launches, "numa_bound": bool(numa_bound), "per_rank": per_rank_diag,
             "e2e": {"value": e2e_value, "unit": "presentations/s", "h2d_bytes_per_step": world * B * WORDS * 32, "d2h_bytes_per_step": world * (B + bitmap_bytes * world),
                     "ms_per_step": e2e_ms_max / args.steps,
                     "api": "ShardedIssuer.verify_wire on ONE global batch of %d x 65,536 items in pinned host memory: contiguous slice per rank -> afx_verify_presentations_wire "

@@ -271,7 +271,7 @@ int afx_multi_issue(afx_multi* m, const afx_request_batch* batch, const afx_issu
  * different issuers, hence different contexts; max_batch of the context = the bucket size; give each shape its own context for
  * full overlap -- shapes sharing one are still correct but take turns).  afx_stream_push takes `n` records: record i is
  * record_bytes(shape_ids[i]) bytes at records + offsets[i]; it is copied into the page-locked bucket of its shape, and a full
- * bucket is submitted asynchronously (afx_*_wire_submit) while the shape's second bucket fills, so bucketing, copies and kernels
+ * bucket is submitted asynchronously (afx_*_wire_submit) while another of the shape's three buckets fills, so bucketing, copies and kernels
  * overlap (the first buckets after a flush are submitted at 1/8, 1/4, 1/2 of the bucket size so that the device starts early).  verdicts[i] is written when the record's bucket retires -- at the latest in afx_stream_flush, which submits the
  * partial buckets and waits for everything; the verdict array of every push must stay valid until then.  The contexts must not
  * be used for other calls between the first push and the flush.  One thread drives a stream. */
