@@ -39,5 +39,48 @@ for n, rk, hide, count in ((4, b"SSPE", [0, 3], 300), (3, b"SES", [1], 70), (16,
     bf[1, 3, 2] ^= 1
     vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes(range(32)))
     assert vr[3] == 1 and vr.sum() == 1 and fb == 1
+    # round 2: item-major prover calls, BatchableProof issuances, RLC bisection, non-canonical wire scalars
+    reqs = np.ascontiguousarray(RequestBatch.from_request(ik, np.ascontiguousarray(issu[:, :n]), R).fields.transpose(1, 0, 2))
+    wout, wst = iss.issue_wire(ik, reqs)
+    assert (wout[:, n:] == out).all() and not iss.verify_wire(ik, wout, issuance=True).any()
+    wp, wps = iss.show_wire(kinds, showin)
+    assert (wp == pres).all()
+    oi, _, tri = orc.verify_issuances(ik, issu, trace=True)
+    bi = np.ascontiguousarray(np.concatenate([issu[:, :n + 3], tri["commitments"], issu[:, n + 4:]], axis=1))
+    assert not iss.verify_issuance_batchable(PresentationBatch.from_items(ik, bi)).any()
+    bi[2, n + 3, 1] ^= 4
+    vr, fb = iss.verify_batchable_rlc(PresentationBatch.from_items(ik, bi), bytes(32), issuance=True)
+    assert vr[2] == 1 and vr.sum() == 1
+    os.environ["AFX_RLC_LEAF"] = "8"
+    vr, fb = iss.verify_batchable_rlc(PresentationBatch(kinds, bf), bytes(32))
+    assert vr[3] == 1 and vr.sum() == 1
+    del os.environ["AFX_RLC_LEAF"]
+    bad = pres[:16].copy()
+    for j in range(16):
+        bad[j, 1 + j % 3, 28:] = np.frombuffer((0xffff0000 + j).to_bytes(4, "little"), np.uint8)      # responses far above l
+    assert iss.verify_wire(kinds, bad).all()
     iss.close()
     print("ok", n, rk)
+
+# the mixed-shape stream object and the multi-device handle (two contexts on device 0)
+from aeonflux_b200.shard import MixedStream, MultiGpuIssuer, interleave_records  # noqa: E402
+sp, ip, sk = C.make_issuer(4)
+orc = C.Issuer(sp, ip, sk)
+k4, p4, i4 = orc.synth(b"SSPE", [0, 3], b"sanitize-stream", 0, 200)
+k2, p2, _ = orc.synth(b"SSPP", [], b"sanitize-stream2", 0, 90, want_issuances=False)
+p4[5, 2, 31] ^= 0x80; p2[7, 1, 0] ^= 1
+order = np.random.default_rng(2).permutation(np.concatenate([np.zeros(200, np.uint8), np.ones(90, np.uint8)]))
+blob, offsets = interleave_records([p4, p2], order)
+a, b = Issuer(sp, ip, sk, device=0, max_batch=64), Issuer(sp, ip, sk, device=0, max_batch=32)
+st = MixedStream()
+st.add_shape(a, k4); st.add_shape(b, k2)
+v = np.full(290, 9, np.uint8)
+st.push(blob, offsets, order, v); st.flush()
+e4, _ = orc.verify_presentations(k4, p4); e2, _ = orc.verify_presentations(k2, p2)
+exp = np.empty(290, np.uint8); exp[order == 0] = e4; exp[order == 1] = e2
+assert (v == exp).all() and exp.sum() == 2
+st.close(); a.close(); b.close()
+m = MultiGpuIssuer(sp, ip, sk, devices=[0, 0], max_batch=64)
+assert (m.verify_wire(k4, p4) == e4).all()
+m.close()
+print("ok stream + multi")
