@@ -461,3 +461,9 @@ def test_rlc_bisection_on_gpu(coracle, monkeypatch):
     from tests.test_host_logic import check_rlc_bisection
     check_rlc_bisection(lambda sp, ip, sk, mb: Issuer(sp, ip, sk, device=0, max_batch=mb), coracle, count=65536, max_batch=65536, leaf=1024, n_bad=3,
                         monkeypatch=monkeypatch)
+
+
+def test_wide_table_allocation_failure_falls_back_on_gpu(coracle, monkeypatch):
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_wide_table_allocation_failure
+    check_wide_table_allocation_failure(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=64), coracle, monkeypatch)

@@ -638,3 +638,29 @@ def check_rlc_bisection(make_issuer, coracle, count, max_batch, leaf, n_bad, mon
 def test_rlc_bisection_on_emulation(emu, coracle, monkeypatch):
     from aeonflux_b200 import Issuer
     check_rlc_bisection(lambda sp, ip, sk, mb: Issuer(sp, ip, sk, max_batch=mb, _binding=emu), coracle, count=70, max_batch=64, leaf=4, n_bad=2, monkeypatch=monkeypatch)
+
+
+def check_wide_table_allocation_failure(make_issuer, coracle, monkeypatch):
+    """afx_ctx_create when the radix-2^16 constant tables cannot be allocated (the fallback was exercised by no test):
+    the context falls back to the radix-4096 tables -- one table-setup launch fewer -- and verifies like any other."""
+    from aeonflux_b200 import PresentationBatch
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"ctab16-fail", 0, 12)
+    pres[3, 1, 31] ^= 0x10; issu[5, 9, 0] ^= 1
+    wide = make_issuer(sp, ip, sk)
+    monkeypatch.setenv("AFX_TEST_FAIL_CTAB16", "1")
+    narrow = make_issuer(sp, ip, sk)
+    monkeypatch.delenv("AFX_TEST_FAIL_CTAB16")
+    assert narrow.launch_count == wide.launch_count - 1
+    ov, _ = orc.verify_presentations(kinds, pres)
+    oi, _ = orc.verify_issuances(bytes([0, 0, 2, 2]), issu)
+    for iss in (wide, narrow):
+        assert (iss.verify_batch(PresentationBatch.from_items(kinds, pres)) == ov).all() and ov.sum() == 1
+        assert (iss.verify_issuance_batch(PresentationBatch.from_items(bytes([0, 0, 2, 2]), issu)) == oi).all() and oi.sum() == 1
+
+
+def test_wide_table_allocation_failure_falls_back(emu, coracle, monkeypatch):
+    from aeonflux_b200 import Issuer
+    monkeypatch.setenv("AFX_HOSTEMU_CTAB16", "1")
+    check_wide_table_allocation_failure(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=16, _binding=emu), coracle, monkeypatch)
