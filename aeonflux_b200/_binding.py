@@ -35,7 +35,8 @@ class Binding:
                "afx_multi_verify_presentations_wire", "afx_multi_verify_issuances", "afx_multi_verify_issuances_wire", "afx_multi_issue",
                "afx_verify_presentations_wire_submit", "afx_verify_issuances_wire_submit", "afx_stream_create", "afx_stream_destroy",
                "afx_stream_add_shape", "afx_stream_push", "afx_stream_flush", "afx_stream_buckets_submitted", "afx_stream_times",
-               "afx_issue_wire", "afx_show_wire", "afx_issuance_batchable_num_fields", "afx_verify_issuances_batchable", "afx_verify_issuances_batchable_rlc", "afx_get_rlc_stats"]
+               "afx_issue_wire", "afx_show_wire", "afx_presentation_linked_num_commitments", "afx_verify_presentations_linked",
+               "afx_verify_presentations_linked_wire", "afx_show_linked", "afx_show_linked_wire", "afx_issuance_batchable_num_fields", "afx_verify_issuances_batchable", "afx_verify_issuances_batchable_rlc", "afx_get_rlc_stats"]
 
     def __init__(self, cdll):
         L = self.L = cdll
@@ -93,7 +94,15 @@ class Binding:
         L.afx_show.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), ctypes.POINTER(afx_issuance_out), vp, ctypes.POINTER(afx_debug_dump)]
         L.afx_show_device.restype = ctypes.c_int
         L.afx_show_device.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp, vp]
-        for f in ("afx_issue_wire", "afx_show_wire"):
+        L.afx_presentation_linked_num_commitments.restype = sz
+        L.afx_presentation_linked_num_commitments.argtypes = [ctypes.c_uint16, ctypes.c_char_p]
+        L.afx_verify_presentations_linked.restype = ctypes.c_int
+        L.afx_verify_presentations_linked.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), vp, ctypes.POINTER(afx_debug_dump)]
+        L.afx_verify_presentations_linked_wire.restype = ctypes.c_int
+        L.afx_verify_presentations_linked_wire.argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp]
+        L.afx_show_linked.restype = ctypes.c_int
+        L.afx_show_linked.argtypes = [vp, ctypes.POINTER(afx_presentation_batch), ctypes.POINTER(afx_issuance_out), vp, ctypes.POINTER(afx_debug_dump)]
+        for f in ("afx_issue_wire", "afx_show_wire", "afx_show_linked_wire"):
             getattr(L, f).restype = ctypes.c_int
             getattr(L, f).argtypes = [vp, ctypes.c_uint16, ctypes.c_char_p, sz, vp, vp, vp]
         L.afx_selftest_primitive.restype = ctypes.c_int

@@ -264,6 +264,10 @@ __global__ void __launch_bounds__(128) k_comb_setup(const u32* enc, u32 ncp, u32
     u32 b = t / (COMB_WINDOWS * COMB_ENTRIES), r = t % (COMB_WINDOWS * COMB_ENTRIES);
     comb_entry_job(enc + 8 * b, r / COMB_ENTRIES, r % COMB_ENTRIES + 1, comb + (size_t)t * 24);
 }
+__global__ void __launch_bounds__(32) k_link_setup(const u32* enc_gy, u32 ny, u32* out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 1 && i < ny) link_entry_job(enc_gy, i, out + 8 * i);
+}
 __global__ void __launch_bounds__(128) k_primitive(u32 op, const u32* in, u32* out, u32* flags, u32 count) {
     u32 item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < count) primitive_job(op, in, out, flags, item);
@@ -447,6 +451,7 @@ static void be_launch_comb_setup(const u32* d_enc, u32 ncp, u32* d_comb, be_stre
     u32 total = ncp * COMB_WINDOWS * COMB_ENTRIES;
     k_comb_setup<<<(total + 127) / 128, 128, 0, s>>>(d_enc, ncp, d_comb);
 }
+static void be_launch_link_setup(const u32* d_enc_gy, u32 ny, u32* d_out, be_stream s) { k_link_setup<<<(ny + 31) / 32, 32, 0, s>>>(d_enc_gy, ny, d_out); }
 static void be_launch_primitive(u32 op, const u32* in, u32* out, u32* flags, u32 count, be_stream s) {
     k_primitive<<<(count + 127) / 128, 128, 0, s>>>(op, in, out, flags, count);
 }

@@ -592,7 +592,9 @@ AFX_HD void out_word_job(const Workspace& ws, const OutWord& d, u32 word, u32 it
 struct CmpPair { u16 commit_slot, field; };
 AFX_HD void commit_compare_job(const Workspace& ws, const CmpPair& p, u32 item) {
     u32 a[8], b[8];
-    load8(a, commit_ptr(ws, p.commit_slot, item)); load8(b, field_ptr(ws, p.field, item));
+    // 0x8000 | field: compare two wire words (linked presentations: C_y[0] must be the proof of encryption's C_y_1)
+    load8(a, (p.commit_slot & 0x8000u) ? field_ptr(ws, p.commit_slot & 0x7fffu, item) : commit_ptr(ws, p.commit_slot, item));
+    load8(b, field_ptr(ws, p.field, item));
     u32 x = 0;
     for (int i = 0; i < 8; i++) x |= a[i] ^ b[i];
     if (x) status_or(ws, item, ST_CHALLENGE);
@@ -947,6 +949,12 @@ AFX_HD void primitive_job(u32 op, const u32* in, u32* out, u32* flags, u32 item)
     }
     for (int i = 0; i < 8; i++) out[(size_t)item * 8 + i] = w[i];
     flags[item] = ok;
+}
+
+// encoding of G_y[i] - G_y[0] (the base of the linked presentation's extra constraint), i = 1..ny-1
+AFX_HD void link_entry_job(const u32* enc_gy /*[ny][8]*/, u32 i, u32* out /*8 words*/) {
+    ge a, b; ge_decompress(a, enc_gy + 8 * i); ge_decompress(b, enc_gy);
+    ge_compress(out, ge_sub(a, b));
 }
 
 // entry (base b, window i, multiple e in 1..8) of the radix-16 comb: (e * 16^i) * P in affine Niels form.

@@ -26,6 +26,7 @@ struct IssuerConsts {
     u32 n = 0, ny = 0;
     std::vector<std::array<uint8_t, 32>> enc;      // compressed encoding of constant point id
     std::vector<std::array<uint8_t, 32>> enc_neg;  // compressed encoding of its negation (filled by device setup)
+    std::vector<std::array<uint8_t, 32>> enc_link; // [ny] encoding of G_y[i] - G_y[0] (linked presentations; filled by device setup; entry 0 unused)
     u32 id_G() const { return 0; }
     u32 id_Gw() const { return 1; }
     u32 id_Gwp() const { return 2; }
@@ -139,6 +140,7 @@ struct ShapeProgram {
     std::vector<CmpPair> cmp_pairs;    // (recomputed commitment slot, wire commitment field)
     std::vector<u16> commit_ext;       // extended-coordinates slot of each wire commitment, same order as cmp_pairs' fields
     std::vector<RlcDesc> rlc;          // one descriptor (batchable mode): inputs / constant terms of the random linear combination
+    std::vector<CmpPair> eq_fields;    // linked presentations: wire words that must be equal (commit_slot = 0x8000 | field a, field = field b)
     std::vector<u32> pre_msms;         // batchable mode: MSM jobs whose outputs the transcript absorbs (tU, M_i of an issuance): they run before it
     bool is_issue = false;             // Issuer::issue: constant-schedule MSMs, derived scalars, output words instead of verdicts
     std::vector<DeriveOp> derived;     // per-item derived scalars, slot k = op k
@@ -252,9 +254,15 @@ inline void build_rlc(ShapeProgram& P) {
 
 // ProofOfValidCredential::verify as a program (presentation.rs:324-443).  batchable = the same statement verified from a
 // BatchableProof (zkp verify_batchable): each challenge word of the layout is replaced by that proof's blinding commitments.
-inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const uint8_t* kinds, bool batchable = false) {
+// linked = the opt-in statement that ties each proof of encryption to the credential proof (the DLEQ the reference leaves as a
+// TODO, README.md:119-122, presentation.rs:292; oracle/pyoracle/aeonflux.py:presentation_prove spells the statement out): per hidden
+// plaintext at index i > 0 two more allocated points, G_y[i] - G_y[0] ("G_y-G_y_1", a per-issuer constant) and C_y[i] - C_y_1
+// ("C_y-C_y_1"), after the G_m points and before Z, and the constraint C_y[i] - C_y_1 = z * (G_y[i] - G_y[0]) after the C_y constraints
+// (evaluated over the existing generators: z*G_y[i] - z*G_y[0] - c*D); at index 0 the two wire words must be equal.  Same wire layout.
+inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const uint8_t* kinds, bool batchable = false, bool linked = false) {
     if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
     for (u32 i = 0; i < n; i++) if (kinds[i] > 3) throw std::invalid_argument("bad attribute kind");
+    if (batchable && linked) throw std::invalid_argument("the linked statement is only built for compact proofs");
     ShapeProgram P;
     // ---- field map
     u32 hs = 0; std::vector<int> ss_rank(n, -1);
@@ -320,6 +328,16 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         es[e].T_CY2P = job((int)(b + 13), -1, PJ_COPY, W_TABLE).table;
         { Slots o = job((int)(b + 10), (int)(b + 9), PJ_SUB, W_TABLE | W_COMP); es[e].T_D = o.table; es[e].C_D = o.comp; }    // C_y_1 - E2 (encryption.rs:183)
     }
+    // linked statement: D_i = C_y[i] - C_y_1 of hidden plaintext i > 0 (ladder base + encoding); at index 0 an equality check
+    struct LinkSlots { u32 attr; int T_D, C_D; };
+    std::vector<LinkSlots> links;
+    if (linked)
+        for (size_t e = 0; e < enc_base.size(); e++) {
+            const u32 idx = enc_attr[e], f_cy1 = enc_base[e] + 10;
+            if (idx == 0) { CmpPair cp; cp.commit_slot = (u16)(0x8000u | (F_CY + 0)); cp.field = (u16)f_cy1; P.eq_fields.push_back(cp); continue; }
+            Slots o = job((int)(F_CY + idx), (int)f_cy1, PJ_SUB, W_TABLE | W_COMP);
+            links.push_back({idx, o.table, o.comp});
+        }
     // ---- aMAC (presentation.rs:342-352)
     P.has_amac = true;
     AmacDesc& A = P.amac; std::memset(&A, 0, sizeof A);
@@ -362,6 +380,10 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         m.var(T_CY[nsp[i]], C_main, true);
         P.msms.push_back(m.d); main_cons.push_back({slot++, "C_y"});
     }
+    for (const LinkSlots& l : links) {      // C_y[i] - C_y_1 = z * (G_y[i] - G_y[0])
+        MsmBuilder m(slot); m.tab2ext = t2e; m.con(ic.id_Gy(l.attr), R_z); m.con(ic.id_Gy(0), R_z, true); m.var((u32)l.T_D, C_main, true);
+        P.msms.push_back(m.d); main_cons.push_back({slot++, "C_y-C_y_1"});
+    }
     {
         TxBuilder tb; tb.start("2019/1416 anonymous credential"); tb.domain_sep("2019/1416 presentation proof");
         tb.scalar_var("z"); tb.scalar_var("z_0"); tb.scalar_var("t");
@@ -372,6 +394,7 @@ inline ShapeProgram compile_presentation(const IssuerConsts& ic, u32 n, const ui
         for (u32 i : nsp) tb.point_var("C_y", SRC_FIELD, F_CY + i);
         for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("G_y", ic.enc[ic.id_Gy(i)].data());
         for (u32 i = 0; i < n; i++) if (kinds[i] == 1) tb.point_var_const("G_m", ic.enc[ic.id_Gm(i)].data());
+        for (const LinkSlots& l : links) { tb.point_var_const("G_y-G_y_1", ic.enc_link.at(l.attr).data()); tb.point_var("C_y-C_y_1", SRC_COMP, (u32)l.C_D); }
         tb.point_var("Z", SRC_COMP, C_Z);
         for (size_t k = 0; k < main_cons.size(); k++) {
             const Con& c = main_cons[k];
@@ -616,7 +639,7 @@ inline size_t show_num_fields(u32 n, const uint8_t* kinds) {
     for (u32 i = 0; i < n; i++) { f += kinds[i] == 3 ? 3 : 1; hs += kinds[i] == 1; hp += kinds[i] == 3; }
     return f + (hp ? 4 : 0) + 2 + 2 * (3 + hs) + 12 * hp;
 }
-inline ShapeProgram compile_show(const IssuerConsts& ic, u32 n, const uint8_t* kinds) {
+inline ShapeProgram compile_show(const IssuerConsts& ic, u32 n, const uint8_t* kinds, bool linked = false) {
     if (n != ic.n || n == 0 || n > MAX_ATTRS) throw std::invalid_argument("attribute count does not match the issuer's");
     for (u32 i = 0; i < n; i++) if (kinds[i] > 3) throw std::invalid_argument("bad attribute kind");
     ShapeProgram P; P.is_issue = true;
@@ -690,6 +713,16 @@ inline ShapeProgram compile_show(const IssuerConsts& ic, u32 n, const uint8_t* k
         if (kinds[i] == 1) m.con(ic.id_Gm(i), R(D_bm[ss_rank[i]]));
         main_cons.push_back({push(m), "C_y"});
     }
+    // linked statement (see compile_presentation): D_i = C_y[i] - C_y_1 = z*G_y[i] - z*G_y[0] and its blinding commitment b_z*(G_y[i] - G_y[0])
+    struct Link { u32 attr, S_D; };
+    std::vector<Link> links;
+    if (linked)
+        for (u32 i = 1; i < n; i++) if (kinds[i] == 3) {
+            u32 S_D;
+            { MsmBuilder m(slot); m.con(ic.id_Gy(i), R(D_z)); m.con(ic.id_Gy(0), R(D_z), true); S_D = push(m); }
+            { MsmBuilder m(slot); m.con(ic.id_Gy(i), R(D_bz)); m.con(ic.id_Gy(0), R(D_bz), true); main_cons.push_back({push(m), "C_y-C_y_1"}); }
+            links.push_back({i, S_D});
+        }
     {
         TxBuilder tb; tb.start("2019/1416 anonymous credential"); tb.domain_sep("2019/1416 presentation proof");
         tb.scalar_var("z"); tb.scalar_var("z_0"); tb.scalar_var("t");
@@ -700,6 +733,7 @@ inline ShapeProgram compile_show(const IssuerConsts& ic, u32 n, const uint8_t* k
         for (u32 i : nsp) tb.point_var("C_y", SRC_COMMIT, S_CY[i], false);
         for (u32 i = 0; i < ic.ny; i++) tb.point_var_const("G_y", ic.enc[ic.id_Gy(i)].data());
         for (u32 i = 0; i < n; i++) if (kinds[i] == 1) tb.point_var_const("G_m", ic.enc[ic.id_Gm(i)].data());
+        for (const Link& l : links) { tb.point_var_const("G_y-G_y_1", ic.enc_link.at(l.attr).data()); tb.point_var("C_y-C_y_1", SRC_COMMIT, l.S_D, false); }
         tb.point_var("Z", SRC_COMMIT, S_Z, false);
         for (const Con& c : main_cons) { tb.blinding_commitment(c.label, c.slot); P.dump_commit.push_back(c.slot); }
         tb.challenge();

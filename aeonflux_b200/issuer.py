@@ -214,8 +214,12 @@ class Issuer:
         self._b.check(rc)
         return (verdicts, out) if debug else verdicts
 
-    def verify_batch(self, batch: PresentationBatch, debug=False):
-        """Batch Issuer::verify (issuer.rs:141-147): verdict 0 = Ok(()), 1 = Err(VerificationFailure)."""
+    def verify_batch(self, batch: PresentationBatch, debug=False, linked=False):
+        """Batch Issuer::verify (issuer.rs:141-147): verdict 0 = Ok(()), 1 = Err(VerificationFailure).  linked: the opt-in statement
+        that ties each proof of encryption to the credential proof (include/aeonflux_b200.h, "Linked presentations")."""
+        if linked:
+            ncm = self._b.L.afx_presentation_linked_num_commitments(len(batch.kinds), batch.kinds)
+            return self._run(self._b.L.afx_verify_presentations_linked, batch, ncm, self.num_proofs(batch.kinds), debug)
         return self._run(self._b.L.afx_verify_presentations, batch, self.num_commitments(batch.kinds), self.num_proofs(batch.kinds), debug)
 
     def submit(self, batch: PresentationBatch, issuance=False):
@@ -267,7 +271,7 @@ class Issuer:
         self._b.check(self._b.L.afx_get_rlc_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
         return int(a.value), int(b.value)
 
-    def verify_wire(self, kinds, items, issuance=False):
+    def verify_wire(self, kinds, items, issuance=False, linked=False):
         """Batch Issuer::verify (or CredentialIssuance::verify) over item-major wire bytes: items = uint8 [count][n_fields][32],
         the concatenation of each item's words.  One H2D copy; no per-field scatter on the host."""
         items = np.ascontiguousarray(items, dtype=np.uint8)
@@ -275,7 +279,7 @@ class Issuer:
         if items.ndim != 3 or items.shape[1:] != (nf, 32):
             raise ValueError("items must be [count][%d][32] bytes for this shape" % nf)
         verdicts = np.zeros(items.shape[0], np.uint8)
-        fn = self._b.L.afx_verify_issuances_wire if issuance else self._b.L.afx_verify_presentations_wire
+        fn = self._b.L.afx_verify_issuances_wire if issuance else self._b.L.afx_verify_presentations_linked_wire if linked else self._b.L.afx_verify_presentations_wire
         self._b.check(fn(self._h, len(kinds), bytes(kinds), items.shape[0], items.ctypes.data, verdicts.ctypes.data))
         return verdicts
 
@@ -312,7 +316,7 @@ class Issuer:
         res = IssuanceBatch(batch.kinds, out)
         return (res, status, dump) if debug else (res, status)
 
-    def show_batch(self, kinds, fields, debug=False):
+    def show_batch(self, kinds, fields, debug=False, linked=False):
         """Batch AnonymousCredential::show (credential.rs:37-46).  kinds: the presentation's attribute kinds; fields: uint8
         [afx_show_num_fields][count][32] in the order documented in include/aeonflux_b200.h (credential, attributes, keypair,
         rng bytes).  Returns (PresentationBatch, status) -- the batch can be passed to verify_batch as is."""
@@ -330,9 +334,11 @@ class Issuer:
         status = np.zeros(count, np.uint8)
         dbg, dump = None, None
         if debug:
-            dump = {"commitments": np.zeros((self.num_commitments(kinds), count, 32), np.uint8), "status": np.zeros(count, np.uint32)}
+            ncm = self._b.L.afx_presentation_linked_num_commitments(len(kinds), kinds) if linked else self.num_commitments(kinds)
+            dump = {"commitments": np.zeros((ncm, count, 32), np.uint8), "status": np.zeros(count, np.uint32)}
             dbg = B.afx_debug_dump(None, dump["commitments"].ctypes.data, None, dump["status"].ctypes.data)
-        self._b.check(self._b.L.afx_show(self._h, ctypes.byref(cb), ctypes.byref(ob), status.ctypes.data, ctypes.byref(dbg) if dbg is not None else None))
+        fn = self._b.L.afx_show_linked if linked else self._b.L.afx_show
+        self._b.check(fn(self._h, ctypes.byref(cb), ctypes.byref(ob), status.ctypes.data, ctypes.byref(dbg) if dbg is not None else None))
         res = PresentationBatch(kinds, out)
         return (res, status, dump) if debug else (res, status)
 
@@ -353,7 +359,7 @@ class Issuer:
         self._b.check(self._b.L.afx_issue_wire(self._h, n, kinds, count, requests.ctypes.data, out.ctypes.data, status.ctypes.data))
         return out, status
 
-    def show_wire(self, kinds, inputs, out=None):
+    def show_wire(self, kinds, inputs, out=None, linked=False):
         """Batch AnonymousCredential::show over item-major inputs uint8 [count][afx_show_num_fields][32] -> (presentations uint8
         [count][n_fields][32] in the layout verify_wire takes, status)."""
         kinds = bytes(kinds)
@@ -365,7 +371,8 @@ class Issuer:
         if out is None:
             out = np.zeros((count, self.num_fields(kinds), 32), np.uint8)
         status = np.zeros(count, np.uint8)
-        self._b.check(self._b.L.afx_show_wire(self._h, len(kinds), kinds, count, inputs.ctypes.data, out.ctypes.data, status.ctypes.data))
+        fn = self._b.L.afx_show_linked_wire if linked else self._b.L.afx_show_wire
+        self._b.check(fn(self._h, len(kinds), kinds, count, inputs.ctypes.data, out.ctypes.data, status.ctypes.data))
         return out, status
 
     def show_batch_device(self, kinds, count, fields_dev_ptr, out_dev_ptr, status_dev_ptr, stream=0):

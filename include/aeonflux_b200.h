@@ -243,6 +243,26 @@ int afx_show_device(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t
 int afx_show_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* inputs, uint8_t* presentations,
                   uint8_t* status);
 
+/* Linked presentations (opt-in; NOT the reference's protocol but the fix its authors left as a TODO: README.md:119-122,
+ * src/nizk/presentation.rs:292 "don't we also need DLEQ between the plaintext here and that in the commitments above?").  In the
+ * reference nothing ties the proof of encryption's commitment C_y_1 = z*G_y[0] + M1 to the credential proof's C_y[i] = z*G_y[i] + M1:
+ * a prover can present a valid credential and attach the encryption of ANOTHER plaintext, and Issuer::verify accepts.  The linked
+ * statement adds to the credential proof, per hidden plaintext attribute at index i > 0, the allocated points G_y[i] - G_y[0] (label
+ * "G_y-G_y_1") and C_y[i] - C_y_1 (label "C_y-C_y_1") -- after the G_m points, before Z -- and the constraint
+ *     C_y[i] - C_y_1 = z * (G_y[i] - G_y[0])        (a DLEQ with Z = z*I: the same z, hence the same M1)
+ * after the C_y constraints; at index 0 both commitments use G_y[0] and the two wire words must be equal.  The wire layout is
+ * unchanged (only challenge and responses differ), so afx_show_linked's output has the presentation layout and
+ * afx_verify_presentations_linked takes it; a presentation made by afx_show / the reference fails the linked verifier and vice versa
+ * (different transcripts), except for shapes without a hidden plaintext at an index > 0.  dbg->commitments then holds
+ * afx_presentation_linked_num_commitments() rows (the link constraints follow the C_y constraints of the main proof). */
+size_t afx_presentation_linked_num_commitments(uint16_t n_attrs, const uint8_t* kinds);
+int afx_verify_presentations_linked(afx_ctx* ctx, const afx_presentation_batch* batch, uint8_t* verdicts, afx_debug_dump* dbg);
+int afx_verify_presentations_linked_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* items,
+                                         uint8_t* verdicts);
+int afx_show_linked(afx_ctx* ctx, const afx_show_batch* batch, const afx_presentation_out* out, uint8_t* status, afx_debug_dump* dbg);
+int afx_show_linked_wire(afx_ctx* ctx, uint16_t n_attrs, const uint8_t* kinds, size_t count, const uint8_t* inputs,
+                         uint8_t* presentations, uint8_t* status);
+
 /* Several B200s behind one handle -- the `devices[], n_devices` form of SURVEY 8b, so that a caller (the Rust shim's
  * Issuer::verify_batch) gets the whole box from one call and builds no threads of its own.  afx_multi_create replicates the
  * issuer context on every listed device (the same arguments as afx_ctx_create; max_batch is per device) and starts one host

@@ -471,10 +471,21 @@ class Presentation:
         self.C_x_0, self.C_x_1, self.C_V, self.C_y = C_x_0, C_x_1, C_V, C_y
 
 
-def presentation_prove(sp, ip, amac, attrs, keypair, z_, blindings, enc_blindings):
+LINK_BASE_LABEL, LINK_LABEL = b"G_y-G_y_1", b"C_y-C_y_1"
+
+
+def presentation_prove(sp, ip, amac, attrs, keypair, z_, blindings, enc_blindings, linked=False):
     """ProofOfValidCredential::prove, presentation.rs:139-321 (via AnonymousCredential::show,
     credential.rs:37-46).  z_, blindings (3+h_s) and enc_blindings (6 per SecretPoint) are
-    supplied (see zkp.py docstring)."""
+    supplied (see zkp.py docstring).
+
+    linked=True is NOT the reference's protocol: it is the fix its authors left as a TODO (README.md:119-122,
+    presentation.rs:292 "don't we also need DLEQ between the plaintext here and that in the commitments above?").  The
+    proof of encryption of hidden plaintext i commits to M1 as C_y_1 = z*G_y[0] + M1 while the credential proof commits to
+    it as C_y[i] = z*G_y[i] + M1, and nothing ties the two.  The linked statement adds, per hidden plaintext at index i > 0,
+    the allocated points G_y[i] - G_y[0] (label "G_y-G_y_1") and C_y[i] - C_y_1 (label "C_y-C_y_1") -- after the G_m
+    points, before Z -- and the constraint  C_y[i] - C_y_1 = z * (G_y[i] - G_y[0])  after the C_y constraints: a DLEQ with
+    Z = z*I.  At index 0 both commitments use G_y[0], so the verifier requires C_y[0] == C_y_1 outright."""
     if keypair is None and any(k == "SP" for k, _ in attrs):
         raise ValueError("NoSymmetricKey")
     z_0_ = (-amac.t * z_) % L
@@ -515,6 +526,14 @@ def presentation_prove(sp, ip, amac, attrs, keypair, z_, blindings, enc_blinding
     G_m = {}
     for i, bp, _m in H_s_:
         G_m[i] = pr.allocate_point(b"G_m", bp)[0]
+    links = []
+    if linked:
+        for i, (k, _v) in enumerate(attrs):
+            if k == "SP" and i > 0:
+                base = sp.G_y[i] - sp.G_y[0]
+                Lv = pr.allocate_point(LINK_BASE_LABEL, base)[0]
+                Dv = pr.allocate_point(LINK_LABEL, base * z_)[0]       # = C_y[i] - C_y_1
+                links.append((Dv, Lv))
     Z, _ = pr.allocate_point(b"Z", Z_)
     pr.constrain(Z, [(z, I)])
     pr.constrain(C_x_1, [(tv, C_x_0), (z_0, G_x_0), (z, G_x_1)])
@@ -528,6 +547,8 @@ def presentation_prove(sp, ip, amac, attrs, keypair, z_, blindings, enc_blinding
             pr.constrain(C_y_i, [(z, G_y[i]), (H_s[i], G_m[i])])
         else:
             pr.constrain(C_y_i, [(z, G_y[i])])
+    for Dv, Lv in links:
+        pr.constrain(Dv, [(z, Lv)])
     assert len(blindings) == len(pr.scalars)
     c, responses, _ = pr.prove_compact(blindings)
     poes, enc_attrs = [], []
@@ -547,10 +568,10 @@ def presentation_prove(sp, ip, amac, attrs, keypair, z_, blindings, enc_blinding
     return Presentation((c, responses), poes, enc_attrs, hidden_scalar_indices, C_x_0_, C_x_1_, C_V_, C_y_)
 
 
-def presentation_verify(p: Presentation, issuer: Issuer, trace=None):
+def presentation_verify(p: Presentation, issuer: Issuer, trace=None, linked=False):
     """ProofOfValidCredential::verify, presentation.rs:324-443.  Raises VerificationFailure
     (the only CredentialError this path can yield) -- or IndexError/KeyError where the
-    Rust panics on structurally malformed input."""
+    Rust panics on structurally malformed input.  linked: see presentation_prove."""
     sp, ip, sk = issuer.system_parameters, issuer.issuer_parameters, issuer.amacs_key
     # :342-352
     Z_ = p.C_V - sk.W - p.C_x_0 * sk.x_0 - p.C_x_1 * sk.x_1
@@ -588,6 +609,19 @@ def presentation_verify(p: Presentation, issuer: Issuer, trace=None):
     G_m = {}
     for i in H_s:
         G_m[i] = vf.allocate_point(b"G_m", sp.G_m[i].compress())
+    links = []
+    if linked:
+        poe_of = dict(p.proofs_of_encryption)
+        for i, (k, _v) in enumerate(p.encrypted_attributes):
+            if k != "SP":
+                continue
+            if i == 0:
+                if p.C_y[0].compress() != poe_of[0].C_y_1.compress():
+                    raise VerificationFailure("C_y[0] is not the proof of encryption's C_y_1")
+                continue
+            Lv = vf.allocate_point(LINK_BASE_LABEL, (sp.G_y[i] - sp.G_y[0]).compress())
+            Dv = vf.allocate_point(LINK_LABEL, (p.C_y[i] - poe_of[i].C_y_1).compress())
+            links.append((Dv, Lv))
     Z = vf.allocate_point(b"Z", Z_.compress())
     vf.constrain(Z, [(z, I)])
     vf.constrain(C_x_1, [(tv, C_x_0), (z_0, G_x_0), (z, G_x_1)])
@@ -599,6 +633,8 @@ def presentation_verify(p: Presentation, issuer: Issuer, trace=None):
             vf.constrain(C_y_i, [(z, G_y[i]), (H_s[i], G_m[i])])
         else:
             vf.constrain(C_y_i, [(z, G_y[i])])
+    for Dv, Lv in links:
+        vf.constrain(Dv, [(z, Lv)])
     vf.verify_compact(*p.proof)
     for _i, poe in p.proofs_of_encryption:  # :438-440
         encryption_verify(poe, sp, trace)

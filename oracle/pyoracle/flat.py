@@ -123,7 +123,7 @@ def words_to_presentation(kinds, words, batchable=False) -> Presentation:
     return Presentation((c, resp), poes, enc_attrs, hidden, C_x_0, C_x_1, C_V, C_y)
 
 
-def verify_flat(issuer, kinds, words, batchable=False):
+def verify_flat(issuer, kinds, words, batchable=False, linked=False):
     """-> (verdict, trace).  verdict 0 = Ok, 1 = VerificationFailure.
     trace: {'Z': bytes, 'commitments': [bytes...] (main proof's then each enc proof's, in
     constraint order), 'challenges': [32-byte recomputed challenge per proof]} -- filled as far
@@ -133,7 +133,7 @@ def verify_flat(issuer, kinds, words, batchable=False):
     verdict = 0
     try:
         p = words_to_presentation(kinds, words, batchable)
-        presentation_verify(p, issuer, trace)
+        presentation_verify(p, issuer, trace, linked=linked)
     except VerificationFailure:
         verdict = 1
     out["Z"] = trace.get("Z")

@@ -139,6 +139,7 @@ static void be_launch_comb_setup(const u32* enc, u32 ncp, u32* comb, be_stream) 
         }
     }
 }
+static void be_launch_link_setup(const u32* enc_gy, u32 ny, u32* out, be_stream) { for (u32 i = 1; i < ny; i++) link_entry_job(enc_gy, i, out + 8 * i); }
 static void be_launch_primitive(u32 op, const u32* in, u32* out, u32* flags, u32 count, be_stream) {
     for (u32 i = 0; i < count; i++) primitive_job(op, in, out, flags, i);
 }

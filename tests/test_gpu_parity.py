@@ -467,3 +467,41 @@ def test_wide_table_allocation_failure_falls_back_on_gpu(coracle, monkeypatch):
     from aeonflux_b200 import Issuer
     from tests.test_host_logic import check_wide_table_allocation_failure
     check_wide_table_allocation_failure(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=64), coracle, monkeypatch)
+
+
+@pytest.mark.parametrize("n,request_,hide,tag", [(4, ("PS", "PS", "PP", "EP"), (0, 3), b"readme4"), (1, ("EP",), (0,), b"plain1"),
+                                                 (5, ("PS", "PP", "EP", "EP", "EP"), (0, 2, 3, 4), b"three")])
+def test_linked_presentations_on_gpu(n, request_, hide, tag):
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_linked_presentations
+    check_linked_presentations(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=8), n, request_, hide, 12, tag)
+
+
+def test_reference_accepts_spliced_encryption_on_gpu():
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_reference_accepts_spliced_encryption
+    check_reference_accepts_spliced_encryption(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=8))
+
+
+def test_linked_full_size_round_trip(readme4):
+    """65,536 linked README-4 presentations made on the device (afx_show_linked) verify under the linked statement, are all rejected by
+    the reference's statement (different transcript), and a flipped bit is caught."""
+    from aeonflux_b200 import Issuer
+    orc, _, (sp, ip, sk) = readme4
+    base = 1024
+    kinds, _, _, showin = orc.synth(b"SSPE", [0, 3], b"linked-full", 0, base, want_issuances=False, want_show_inputs=True)
+    count = 65536
+    fields = np.tile(np.ascontiguousarray(showin.transpose(1, 0, 2)), (1, count // base, 1))
+    fields[-22:] = np.random.default_rng(5).integers(0, 256, (22, count, 32), dtype=np.uint8)      # fresh z and blindings for every item
+    iss = Issuer(sp, ip, sk, device=0, max_batch=count)
+    res, st = iss.show_batch(kinds, fields, linked=True)
+    assert not st.any()
+    wire = np.ascontiguousarray(res.fields.transpose(1, 0, 2))
+    assert not iss.verify_wire(kinds, wire, linked=True).any()
+    assert iss.verify_wire(kinds, wire[:4096]).all()
+    rng = np.random.default_rng(6)
+    bad = rng.choice(count, 200, replace=False)
+    for i in bad:
+        wire[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+    expect = np.zeros(count, np.uint8); expect[bad] = 1
+    assert (iss.verify_wire(kinds, wire, linked=True) == expect).all()

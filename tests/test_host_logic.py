@@ -664,3 +664,121 @@ def test_wide_table_allocation_failure_falls_back(emu, coracle, monkeypatch):
     from aeonflux_b200 import Issuer
     monkeypatch.setenv("AFX_HOSTEMU_CTAB16", "1")
     check_wide_table_allocation_failure(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=16, _binding=emu), coracle, monkeypatch)
+
+
+def linked_case(n, request, hide, count, tag, linked=True):
+    """Python-oracle material for the linked (DLEQ) presentation tests: issuer bytes, kinds, the struct-of-arrays show input
+    [n_show_fields][count][32], the linked presentations the oracle's prover makes from the same rng bytes [count][W][32], and for every
+    item a SPLICED copy: the same credential proof with the proof of encryption of another plaintext (same z) attached."""
+    from oracle.pyoracle import aeonflux as A, flat as F, ristretto as R, synth as S
+    iss = S.make_issuer(n)
+    sp, ip = iss.system_parameters, iss.issuer_parameters
+    rng = A.ShakeRng(b"linked/" + tag)
+    kinds = None
+    rows, pres, spliced = [], [], []
+    for _ in range(count):
+        attrs = []
+        for k in request:
+            attrs.append(("PS", rng.scalar()) if k == "PS" else ("PP", rng.point()) if k == "PP" else ("EP", A.Plaintext.from_bytes30(rng.fill(30))))
+        _, (amac, _) = iss.issue(list(attrs), rng)
+        kp, _ = A.SymmetricKeypair.generate(sp, rng)
+        shown = list(attrs)
+        for i in hide:
+            A.hide_attribute(shown, i)
+        h_s, h_p = sum(k == "SS" for k, _ in shown), sum(k == "SP" for k, _ in shown)
+        draws = [rng.fill(64) for _ in range(1 + 3 + h_s + 6 * h_p)]
+        sc = [R.sc_from_wide(d) for d in draws]
+        p = A.presentation_prove(sp, ip, amac, shown, kp if h_p else None, sc[0], sc[1:4 + h_s], [sc[4 + h_s + 6 * e:10 + h_s + 6 * e] for e in range(h_p)], linked=linked)
+        kinds = F.presentation_kinds(p)
+        pres.append(F.presentation_to_words(p))
+        w = [R.sc_to_bytes(amac.t), amac.U.compress(), amac.V.compress()]
+        for k, v in shown:
+            w += [R.sc_to_bytes(v)] if k in ("PS", "SS") else [v.compress()] if k == "PP" else [v.M1.compress()] if k == "EP" else [v.M1.compress(), v.M2.compress(), R.sc_to_bytes(v.m3)]
+        if h_p:
+            w += [R.sc_to_bytes(kp.a), R.sc_to_bytes(kp.a0), R.sc_to_bytes(kp.a1), kp.pk.compress()]
+        for d in draws:
+            w += [d[:32], d[32:]]
+        rows.append(w)
+        if h_p:
+            other = A.Plaintext.from_bytes30(rng.fill(30))
+            i = [j for j, (k, _) in enumerate(shown) if k == "SP"][0]
+            p.proofs_of_encryption[0] = (i, A.encryption_prove(sp, other, i, kp, sc[0], [rng.scalar() for _ in range(6)]))
+            spliced.append(F.presentation_to_words(p))
+    tow = lambda items: np.frombuffer(b"".join(b"".join(ws) for ws in items), np.uint8).reshape(len(items), -1, 32).copy()
+    show_in = np.ascontiguousarray(tow(rows).transpose(1, 0, 2))
+    return iss, bytes(kinds), show_in, tow(pres), (tow(spliced) if spliced else None)
+
+
+def check_linked_presentations(make_issuer, n, request, hide, count, tag):
+    """The linked statement (README.md:119-122's TODO, opt-in): afx_show_linked is byte-identical to the oracle's linked prover,
+    afx_verify_presentations_linked accepts it with the oracle's Z / commitments / challenges, the reference's verifier and the linked
+    one reject each other's proofs (different transcripts) -- and a credential proof with the encryption of ANOTHER plaintext attached,
+    which Issuer::verify accepts, is rejected by the linked verifier."""
+    from aeonflux_b200 import PresentationBatch
+    from oracle.pyoracle import flat as F
+    from tests.common import compare_with_oracle_trace
+    iss, kinds, show_in, pres, spliced = linked_case(n, request, hide, count, tag)
+    sp, ip, sk = iss.system_parameters.to_bytes(), iss.issuer_parameters.to_bytes(), iss.amacs_key.to_bytes()
+    eng = make_issuer(sp, ip, sk)
+    user = make_issuer(sp, ip, None)
+    res, st, sdbg = user.show_batch(kinds, show_in, debug=True, linked=True)
+    assert not st.any()
+    got = res.fields.transpose(1, 0, 2)
+    assert (got == pres).all(), "afx_show_linked differs from the oracle's linked prover"
+    wgot, wst = user.show_wire(kinds, np.ascontiguousarray(show_in.transpose(1, 0, 2)), linked=True)
+    assert (wgot == pres).all() and not wst.any()
+    has_link = any(k == 3 and i > 0 for i, k in enumerate(kinds))
+    # linked verifier vs oracle: verdicts, Z, every commitment (incl. the link constraints), challenges
+    pres[1 % count, 1, 0] ^= 1
+    items = np.concatenate([pres] + ([spliced] if spliced is not None else []))
+    overd, otr = zip(*[F.verify_flat(iss, kinds, [items[i, w].tobytes() for w in range(items.shape[1])], linked=True) for i in range(len(items))])
+    ncm = eng._b.L.afx_presentation_linked_num_commitments(len(kinds), kinds)
+    tr = {"Z": np.zeros((len(items), 32), np.uint8), "commitments": np.zeros((len(items), ncm, 32), np.uint8),
+          "challenges": np.zeros((len(items), eng.num_proofs(kinds), 32), np.uint8)}
+    for i, t in enumerate(otr):
+        if t["Z"]:
+            tr["Z"][i] = np.frombuffer(t["Z"], np.uint8)
+        for k, cm in enumerate(t["commitments"]):
+            tr["commitments"][i, k] = np.frombuffer(cm, np.uint8)
+        for k, ch in enumerate(t["challenges"]):
+            tr["challenges"][i, k] = np.frombuffer(ch, np.uint8)
+    v, dbg = eng.verify_batch(PresentationBatch.from_items(kinds, items), debug=True, linked=True)
+    # the flat trace lists the main proof's commitments then each enc proof's; the engine's dump has the same order
+    compare_with_oracle_trace(v, dbg, np.array(overd, np.uint8), tr)
+    expect = np.zeros(len(items), np.uint8); expect[1 % count] = 1
+    if spliced is not None:
+        expect[count:] = 1 if has_link or kinds[0] == 3 else 0
+    assert (v == expect).all(), (list(v), list(expect))
+    assert (eng.verify_wire(kinds, items, linked=True) == expect).all()
+    # the reference's verifier: accepts the spliced proofs when they were made by ITS prover -- shown here on the linked prover's
+    # output only where the two statements coincide (no link constraint); otherwise the transcripts differ and it rejects
+    ref = eng.verify_batch(PresentationBatch.from_items(kinds, pres))
+    if has_link:
+        assert ref.all()
+    else:
+        assert list(ref) == list(expect[:count])
+
+
+@pytest.mark.parametrize("n,request_,hide,tag", [(4, ("PS", "PS", "PP", "EP"), (0, 3), b"readme4"), (1, ("EP",), (0,), b"plain1"),
+                                                 (3, ("PS", "EP", "PS"), (1,), b"middle"), (5, ("PS", "PP", "EP", "EP", "EP"), (0, 2, 3, 4), b"three")])
+def test_linked_presentations_on_emulation(emu, n, request_, hide, tag):
+    from aeonflux_b200 import Issuer
+    check_linked_presentations(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=3, _binding=emu), n, request_, hide, 4, tag)
+
+
+def check_reference_accepts_spliced_encryption(make_issuer):
+    """Why the link exists: under the REFERENCE's statement a valid credential proof with the proof of encryption of another
+    plaintext attached is accepted (presentation.rs:292 TODO) -- by the oracle and, bit for bit, by the engine's Issuer::verify."""
+    from aeonflux_b200 import PresentationBatch
+    from oracle.pyoracle import flat as F
+    iss, kinds, _, pres, spliced = linked_case(4, ("PS", "PS", "PP", "EP"), (0, 3), 3, b"unlinked", linked=False)
+    sp, ip, sk = iss.system_parameters.to_bytes(), iss.issuer_parameters.to_bytes(), iss.amacs_key.to_bytes()
+    eng = make_issuer(sp, ip, sk)
+    assert [F.verify_flat(iss, kinds, [spliced[i, w].tobytes() for w in range(spliced.shape[1])])[0] for i in range(3)] == [0, 0, 0]
+    assert not eng.verify_batch(PresentationBatch.from_items(kinds, spliced)).any()
+    assert eng.verify_batch(PresentationBatch.from_items(kinds, spliced), linked=True).all()
+
+
+def test_reference_accepts_spliced_encryption_on_emulation(emu):
+    from aeonflux_b200 import Issuer
+    check_reference_accepts_spliced_encryption(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=3, _binding=emu))
