@@ -336,6 +336,16 @@ static int be_bind_thread_to_device(int device) {
     if (!any) return 1;
     return sched_setaffinity(0, sizeof set, &set) != 0;
 }
+// Device-side address of a host pointer if it lies in page-locked memory the device can read directly (cudaHostAlloc / afx_host_alloc /
+// cudaHostRegister under unified addressing), else null.  AFX_NO_ZERO_COPY in the environment disables it (A/B measurements).
+static const void* be_host_device_pointer(const void* p) {
+    static const bool off = std::getenv("AFX_NO_ZERO_COPY") != nullptr;
+    if (off) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+static size_t be_zero_copy_min_items() { return 4096; }     // below this a call is launch-bound and the plain copy is as good
 typedef cudaEvent_t be_event;
 static void be_event_create(be_event* e) { cudaEventCreate(e); }
 static void be_event_destroy(be_event e) { cudaEventDestroy(e); }
