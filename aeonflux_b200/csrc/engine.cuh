@@ -103,8 +103,6 @@ struct Workspace {
     const u32* fields;   // struct-of-arrays [n_fields][count][8] (fs_field = count, fs_item = 1) or item-major "wire"
                          // [count][n_fields][8] (fs_field = 1, fs_item = n_fields); strides in 32-byte words
     u32 fs_field, fs_item;
-    u32* stage;          // non-null: `fields` is the caller's page-locked host memory; every word a job reads is also stored here (same strides),
-                         // so that the later stages find the batch on the device without a separate copy
     u32 no_tables;       // 1: point jobs skip the standard ladder tables (BatchableProof RLC pass: only its exact fallback walks them)
     u32* tables;         // [n_tables][count][8 entries][32]
     u32* atabs;          // [n_atabs][ceil(count/32)][8 entries][8 quads][32 lanes][4]  aMAC tables, warp-transposed
@@ -200,11 +198,6 @@ struct TableStore {
 AFX_HD void store_table8(u32* dst, const ge& p, u32* tdst = nullptr) { TableStore ts{dst, tdst}; ge_table8(p, ts); }
 
 AFX_HD const u32* field_ptr(const Workspace& ws, u32 f, u32 item) { return ws.fields + ((size_t)f * ws.fs_field + (size_t)item * ws.fs_item) * 8; }
-// load an input word; when the batch is being staged in from host memory, leave a copy on the device
-AFX_HD void load_field(const Workspace& ws, u32 f, u32 item, u32* w) {
-    load8(w, field_ptr(ws, f, item));
-    if (ws.stage) store8(ws.stage + ((size_t)f * ws.fs_field + (size_t)item * ws.fs_item) * 8, w);
-}
 AFX_HD u32* table_ptr(const Workspace& ws, u32 slot, u32 item) { return ws.tables + ((size_t)slot * ws.count + item) * 256; }
 AFX_HD u32* atab_ptr(const Workspace& ws, u32 slot, u32 item) {
     size_t nblk = ((size_t)ws.count + 31) / 32;
@@ -248,7 +241,7 @@ AFX_HD sc eval_scalar(const Workspace& ws, const ScalarSrc& s, u32 item) {
 
 // ---- stage: scalar canonicity ------------------------------------------------------------------------
 AFX_HD void scalar_check_job(const Workspace& ws, u32 field, u32 item) {
-    u32 w[8]; load_field(ws, field, item, w);
+    u32 w[8]; load8(w, field_ptr(ws, field, item));
     if (!sc_is_canonical(sc_from_words(w))) status_or(ws, item, ST_BAD_SCALAR);
 }
 
@@ -260,15 +253,15 @@ AFX_HD void points_job(const Workspace& ws, const PointJob& j, u32 item) {
     const u32 op = j.op & PJ_OP_MASK;
     if (op == PJ_UNIFORM) {       // RistrettoPoint::random: 64 rng bytes through the Elligator map twice (amacs.rs:290)
         u32 u[16];
-        load_field(ws, (u32)j.field_a, item, u); load_field(ws, (u32)j.field_b, item, u + 8);
+        load8(u, field_ptr(ws, (u32)j.field_a, item)); load8(u + 8, field_ptr(ws, (u32)j.field_b, item));
         p = ge_from_uniform(u);
     } else {
-        load_field(ws, (u32)j.field_a, item, w);
+        load8(w, field_ptr(ws, (u32)j.field_a, item));
         ok = ge_decompress(p, w);
     }
     if (op == PJ_ADD || op == PJ_SUB) {
         ge q;
-        load_field(ws, (u32)j.field_b, item, w);
+        load8(w, field_ptr(ws, (u32)j.field_b, item));
         ok &= ge_decompress(q, w);
         p = (op == PJ_ADD) ? ge_add(p, q) : ge_sub(p, q);
     }
