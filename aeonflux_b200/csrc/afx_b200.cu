@@ -28,13 +28,13 @@ constexpr int TPB_MSM = AFX_TPB_MSM;
 constexpr size_t LADDER_SMEM_BUDGET = (size_t)(200 / AFX_MSM_MINB) * 1024;   // per CTA, so that AFX_MSM_MINB CTAs fit one SM
 
 __global__ void __launch_bounds__(256) k_scalar_check(Workspace ws, const u16* fields) {
-    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < ws.count) scalar_check_job(ws, fields[blockIdx.y], item);
+    u32 item = ws.e_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.e_hi) scalar_check_job(ws, fields[blockIdx.y], item);
 }
 
 __global__ void __launch_bounds__(TPB, 4) k_points(Workspace ws, const PointJob* jobs) {
-    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item < ws.count) points_job(ws, jobs[blockIdx.y], item);
+    u32 item = ws.e_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.e_hi) points_job(ws, jobs[blockIdx.y], item);
 }
 
 // All ladders of a verify pipeline in ONE launch: the aMAC ladder (when the shape has one) and the constraint MSMs.
@@ -368,10 +368,10 @@ static void be_host_free(void* p) { cudaFreeHost(p); }
 static dim3 grid_for(u32 count, u32 tpb, u32 y) { return dim3((count + tpb - 1) / tpb, y, 1); }
 
 static void be_launch_scalar_check(const Workspace& ws, const u16* d_fields, u32 nf, be_stream s) {
-    k_scalar_check<<<grid_for(ws.count, 256, nf), 256, 0, s>>>(ws, d_fields);
+    k_scalar_check<<<grid_for(ws.e_hi - ws.e_lo, 256, nf), 256, 0, s>>>(ws, d_fields);
 }
 static void be_launch_points(const Workspace& ws, const PointJob* d_jobs, u32 njobs, be_stream s) {
-    k_points<<<grid_for(ws.count, TPB, njobs), TPB, 0, s>>>(ws, d_jobs);
+    k_points<<<grid_for(ws.e_hi - ws.e_lo, TPB, njobs), TPB, 0, s>>>(ws, d_jobs);
 }
 // The opt-in to > 48 KiB of dynamic shared memory is a per-device function attribute: set it once per (kernel, device).
 static void allow_large_smem(const void* kernel, int which) {

@@ -103,6 +103,7 @@ struct Workspace {
     const u32* fields;   // struct-of-arrays [n_fields][count][8] (fs_field = count, fs_item = 1) or item-major "wire"
                          // [count][n_fields][8] (fs_field = 1, fs_item = n_fields); strides in 32-byte words
     u32 fs_field, fs_item;
+    u32 e_lo, e_hi;      // the early stages (scalar checks, point jobs) of this launch cover items [e_lo, e_hi) only (a batch copied in halves)
     u32 no_tables;       // 1: point jobs skip the standard ladder tables (BatchableProof RLC pass: only its exact fallback walks them)
     u32* tables;         // [n_tables][count][8 entries][32]
     u32* atabs;          // [n_atabs][ceil(count/32)][8 entries][8 quads][32 lanes][4]  aMAC tables, warp-transposed

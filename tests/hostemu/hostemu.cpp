@@ -23,7 +23,7 @@ static int be_d2d(void* d, const void* s, size_t n, be_stream) { std::memcpy(d, 
 static int be_os_random(void* p, size_t n) { FILE* f = std::fopen("/dev/urandom", "rb"); if (!f) return 1; size_t k = std::fread(p, 1, n, f); std::fclose(f); return k != n; }
 static int be_bind_thread_to_device(int) { return 1; }
 static size_t be_zero_copy_min_items() { return 1; }
-static const void* be_host_device_pointer(const void* p) { return p; }     // the emulation "device" reads host memory: exercises the in-place front path
+static const void* be_host_device_pointer(const void* p) { const char* e = std::getenv("AFX_ZERO_COPY"); return (e && *e == '0') ? nullptr : p; }     // the emulation "device" reads host memory: exercises the in-place front path
 static int be_memset(void* d, int v, size_t n, be_stream) { std::memset(d, v, n); return 0; }
 static int be_sync(be_stream) { return 0; }
 static int be_check_launch() { return 0; }
@@ -40,10 +40,10 @@ static int be_host_alloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 16); 
 static void be_host_free(void* p) { std::free(p); }
 
 static void be_launch_scalar_check(const Workspace& ws, const u16* f, u32 nf, be_stream) {
-    for (u32 k = 0; k < nf; k++) for (u32 i = 0; i < ws.count; i++) scalar_check_job(ws, f[k], i);
+    for (u32 k = 0; k < nf; k++) for (u32 i = ws.e_lo; i < ws.e_hi; i++) scalar_check_job(ws, f[k], i);
 }
 static void be_launch_points(const Workspace& ws, const PointJob* jobs, u32 nj, be_stream) {
-    for (u32 k = 0; k < nj; k++) for (u32 i = 0; i < ws.count; i++) points_job(ws, jobs[k], i);
+    for (u32 k = 0; k < nj; k++) for (u32 i = ws.e_lo; i < ws.e_hi; i++) points_job(ws, jobs[k], i);
 }
 static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 nps, const MsmDesc* msms, const u32* idx, u32 nidx, u32, u32 max_terms, u32,
                              int, u32*, u32, u32, u32*, be_stream) {

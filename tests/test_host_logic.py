@@ -782,3 +782,21 @@ def check_reference_accepts_spliced_encryption(make_issuer):
 def test_reference_accepts_spliced_encryption_on_emulation(emu):
     from aeonflux_b200 import Issuer
     check_reference_accepts_spliced_encryption(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=3, _binding=emu))
+
+
+@pytest.mark.parametrize("zero_copy", ["0", "1"])
+def test_single_pass_wire_call_forms(emu, coracle, monkeypatch, zero_copy):
+    """A one-pass item-major host call either copies its batch in two halves (the first half's early stages under the second half's
+    copy) or lets the point jobs read the caller's buffer in place: same verdicts as the struct-of-arrays call, odd counts included."""
+    from aeonflux_b200 import Issuer, PresentationBatch
+    monkeypatch.setenv("AFX_ZERO_COPY", zero_copy)
+    sp, ip, sk = coracle.make_issuer(4)
+    orc = coracle.Issuer(sp, ip, sk)
+    kinds, pres, issu = orc.synth(b"SSPE", [0, 3], b"halves", 0, 9)
+    pres[0, 1, 0] ^= 1; pres[4, 9, 31] ^= 0x80; pres[8, 20, 5] ^= 2; issu[5, 8, 0] ^= 1
+    ov, _ = orc.verify_presentations(kinds, pres)
+    oi, _ = orc.verify_issuances(bytes([0, 0, 2, 2]), issu)
+    iss = Issuer(sp, ip, sk, max_batch=16, _binding=emu)
+    for m in (9, 8, 3, 2, 1):
+        assert (iss.verify_wire(kinds, pres[:m]) == ov[:m]).all(), m
+    assert (iss.verify_wire(bytes([0, 0, 2, 2]), issu, issuance=True) == oi).all() and list(ov) == [1, 0, 0, 0, 1, 0, 0, 0, 1]
