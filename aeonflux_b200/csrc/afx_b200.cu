@@ -336,24 +336,7 @@ static int be_bind_thread_to_device(int device) {
     if (!any) return 1;
     return sched_setaffinity(0, sizeof set, &set) != 0;
 }
-// Device-side address of a host pointer if it lies in page-locked memory the device can read directly (cudaHostAlloc / afx_host_alloc /
-// cudaHostRegister under unified addressing), else null.  In-place reads put the batch on the bus twice (the point jobs' loads and the
-// copy engine's transfer), which pays when the bus has headroom and costs when it is contended -- measured: one GPU, 65,536
-// README-4 items per call 25.84 -> 25.26 ms; eight ranks on one box 27.56 -> 28.61 ms.  So the default is on only when the host has
-// a single visible GPU; AFX_ZERO_COPY=1 / 0 in the environment forces it.
-static const void* be_host_device_pointer(const void* p) {
-    static const int mode = [] {
-        const char* e = std::getenv("AFX_ZERO_COPY");
-        if (e && (*e == '0' || *e == '1')) return *e - '0';
-        int n = 0;
-        return (cudaGetDeviceCount(&n) == cudaSuccess && n == 1) ? 1 : 0;
-    }();
-    if (!mode) return nullptr;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
-    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
-}
-static size_t be_zero_copy_min_items() { return 4096; }     // below this a call is launch-bound and the plain copy is as good
+static size_t be_split_copy_min_items() { return 8192; }     // below this a call is launch-bound and one copy is as good
 typedef cudaEvent_t be_event;
 static void be_event_create(be_event* e) { cudaEventCreate(e); }
 static void be_event_destroy(be_event e) { cudaEventDestroy(e); }

@@ -22,8 +22,7 @@ static int be_d2h(void* h, const void* d, size_t n, be_stream) { std::memcpy(h, 
 static int be_d2d(void* d, const void* s, size_t n, be_stream) { std::memcpy(d, s, n); return 0; }
 static int be_os_random(void* p, size_t n) { FILE* f = std::fopen("/dev/urandom", "rb"); if (!f) return 1; size_t k = std::fread(p, 1, n, f); std::fclose(f); return k != n; }
 static int be_bind_thread_to_device(int) { return 1; }
-static size_t be_zero_copy_min_items() { return 1; }
-static const void* be_host_device_pointer(const void* p) { const char* e = std::getenv("AFX_ZERO_COPY"); return (e && *e == '0') ? nullptr : p; }     // the emulation "device" reads host memory: exercises the in-place front path
+static size_t be_split_copy_min_items() { return 2; }
 static int be_memset(void* d, int v, size_t n, be_stream) { std::memset(d, v, n); return 0; }
 static int be_sync(be_stream) { return 0; }
 static int be_check_launch() { return 0; }
