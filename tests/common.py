@@ -154,3 +154,86 @@ def noncanonical_scalar_batch(items, scalar_words, rng):
             it[w, 28:] = np.frombuffer(int(top).to_bytes(4, "little"), np.uint8)
             out.append(it)
     return np.stack(out)
+
+
+_L = 2**252 + 27742317777372353535851937790883648493
+_P = 2**255 - 19
+
+
+def _w(v):
+    return np.frombuffer(int(v % 2**256).to_bytes(32, "little"), np.uint8)
+
+
+# 32-byte values that sit on the edges of the wire rules (RFC 9496 decode: s < p, s non-negative, a square root exists, the result's
+# T non-negative and Y non-zero; scalars: < l) -- each is a legal scalar or point encoding in some word and an illegal one in another
+EDGE_WORDS = [_w(v) for v in (0, 1, 2, 3, 4, _L - 1, _L, _L + 1, 2 * _L, 8 * _L - 1, 2**252, 2**252 - 1, _P - 1, _P, _P + 1, _P + 2, 2**255 - 20,
+                              2**255 - 1, 2**255, 2**255 + 1, 2**256 - 1, 2**256 - 38, (_P - 1) // 2, (_P + 1) // 2)] + [
+    np.frombuffer(bytes.fromhex(h), np.uint8) for h in (
+        "e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76",      # the ristretto255 basepoint
+        "6a493210f7499cd17fecb510ae0cea23a110e8d5b901f8acadd3095c73a3b919",      # 2B
+        "ecffffffffffffffffffffffffffffffffffffffffffffffffffffffffffff7f",      # p - 1: s = -1, non-canonical sign
+        "0100000000000000000000000000000000000000000000000000000000000080")]     # bit 255 set
+
+
+def fuzz_mutations(items, rng, count, max_mut=3):
+    """count mutated copies of honest items [m][W][32] for differential runs (engine vs oracle): 1..max_mut words of each copy are
+    replaced by an edge value, random bytes, a word from another position of the same item (a valid encoding in the wrong
+    place), the same word of another item, or get one bit flipped (any bit, the top byte's included)."""
+    m, W, _ = items.shape
+    out = np.empty((count, W, 32), np.uint8)
+    for i in range(count):
+        it = items[int(rng.integers(m))].copy()
+        for _ in range(int(rng.integers(1, max_mut + 1))):
+            w, how = int(rng.integers(W)), int(rng.integers(6))
+            if how == 0:
+                it[w] = EDGE_WORDS[int(rng.integers(len(EDGE_WORDS)))]
+            elif how == 1:
+                it[w] = rng.integers(0, 256, 32, dtype=np.uint8)
+            elif how == 2:
+                it[w] = it[int(rng.integers(W))]
+            elif how == 3:
+                it[w] = items[int(rng.integers(m)), w]
+            elif how == 4:
+                it[w, int(rng.integers(32))] ^= 1 << int(rng.integers(8))
+            else:
+                it[w, 31] ^= 1 << int(rng.integers(4, 8))          # the bits that decide s < p / scalar < l
+        out[i] = it
+    return out
+
+
+def differential_fuzz(make_issuer, coracle, seed, count, shapes=((4, b"SSPE", [0, 3]), (3, b"SPE", [2])), with_trace=True):
+    """Mutated presentations and issuances through Issuer::verify / CredentialIssuance::verify of the engine and of the C oracle:
+    identical verdicts and (where the oracle's early return got that far) identical Z, commitments and challenges; then the same
+    context still accepts the honest items.  Returns (accepted, rejected) over everything that was run."""
+    from aeonflux_b200 import PresentationBatch
+    rng = np.random.default_rng(seed)
+    acc = rej = 0
+    for n, rk, hide in shapes:
+        sp, ip, sk = coracle.make_issuer(n)
+        orc = coracle.Issuer(sp, ip, sk)
+        kinds, pres, issu = orc.synth(rk, hide, b"fuzz-%d" % seed, 0, 16)
+        iss = make_issuer(sp, ip, sk)
+        bad = fuzz_mutations(pres, rng, count)
+        ov, _, tr = orc.verify_presentations(kinds, bad, trace=True)
+        if with_trace:
+            v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, bad), debug=True)
+            compare_with_oracle_trace(v, dbg, ov, tr)
+        else:
+            v = iss.verify_batch(PresentationBatch.from_items(kinds, bad))
+            assert (v == ov).all(), np.where(v != ov)[0][:10]
+        assert (iss.verify_wire(kinds, bad) == ov).all()
+        acc += int((ov == 0).sum()); rej += int((ov == 1).sum())
+        ik = bytes(0 if c == ord("S") else 2 for c in rk)
+        ibad = fuzz_mutations(issu, rng, count)
+        oi, _, tri = orc.verify_issuances(ik, ibad, trace=True)
+        if with_trace:
+            vi, dbgi = iss.verify_issuance_batch(PresentationBatch.from_items(ik, ibad), debug=True)
+            compare_with_oracle_trace(vi, dbgi, oi, tri)
+        else:
+            vi = iss.verify_issuance_batch(PresentationBatch.from_items(ik, ibad))
+            assert (vi == oi).all(), np.where(vi != oi)[0][:10]
+        acc += int((oi == 0).sum()); rej += int((oi == 1).sum())
+        assert not iss.verify_batch(PresentationBatch.from_items(kinds, pres)).any()
+        assert not iss.verify_issuance_batch(PresentationBatch.from_items(ik, issu)).any()
+        iss.close()
+    return acc, rej
