@@ -25,6 +25,22 @@ namespace afx {
 #ifndef AFX_SYNC_MASK
 #define AFX_SYNC_MASK 0   // ladder CTAs re-align at a barrier every (AFX_SYNC_MASK + 1) windows
 #endif
+// The constant-schedule ladders (k_msm_ct) stall on their table scans; their barrier policy is separate from the verify ladders':
+// AFX_CT_SYNC_MASK as above, AFX_CT_SYNC_GROUPS = 2 re-aligns each half of the CTA on its own named barrier so that one half can
+// scan while the other multiplies.
+#ifndef AFX_CT_SYNC_MASK
+#define AFX_CT_SYNC_MASK 0
+#endif
+#ifndef AFX_CT_SYNC_GROUPS
+#define AFX_CT_SYNC_GROUPS 1
+#endif
+#if defined(__CUDA_ARCH__) && AFX_CT_SYNC_GROUPS == 2
+#define AFX_CT_STEP_SYNC() do { if (threadIdx.x < 128u) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory"); } while (0)   /* TPB_MSM = 256 */
+#elif defined(__CUDA_ARCH__) && AFX_CT_SYNC_GROUPS == 0
+#define AFX_CT_STEP_SYNC() do { } while (0)
+#else
+#define AFX_CT_STEP_SYNC() AFX_STEP_SYNC()
+#endif
 constexpr int MAX_ATTRS = 32;
 constexpr int MAX_VAR_TERMS = MAX_ATTRS + 4;
 constexpr int MAX_CONST_TERMS = MAX_ATTRS + 8;
@@ -323,7 +339,11 @@ AFX_HD pniels pniels_scan_select_t(const u32* tab, int digit, u32 xneg = 0) {
 AFX_HD void prefetch_atab(const u32* tab_lane0) {
 #if defined(__CUDA_ARCH__)
     const u32* base = tab_lane0 + (threadIdx.x & 31u) * 8 * 32;   // lane's 8 consecutive 128-byte lines
+#ifdef AFX_CT_PREFETCH_L1
+    for (int j = 0; j < 8; j++) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 32 * j));
+#else
     for (int j = 0; j < 8; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 32 * j));
+#endif
 #else
     (void)tab_lane0;
 #endif
@@ -517,7 +537,7 @@ AFX_HD void msm_ct_job(const Workspace& ws, const MsmDesc& d, u32 item, u32* scr
     gc cacc = gc_identity();
     for (int i = 63; i >= 0; i--) {
 #if defined(__CUDA_ARCH__)
-        if ((i & AFX_SYNC_MASK) == AFX_SYNC_MASK) AFX_STEP_SYNC();
+        if ((i & AFX_CT_SYNC_MASK) == AFX_CT_SYNC_MASK) AFX_CT_STEP_SYNC();
 #endif
         if (i != 63) gc_dbl4(cacc);
 #if defined(__CUDA_ARCH__) && defined(AFX_SYNC_FINE)
