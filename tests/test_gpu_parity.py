@@ -156,6 +156,35 @@ def test_full_size_batch_round_trip_properties(readme4):
     assert (v[sample] == ov).all()
 
 
+def test_s16_full_size_round_trip_properties(coracle):
+    """BASELINE config 4 size (65,536 x S16: 16 attributes, 8 hidden plaintexts, 4,576 bytes per item) through the same properties:
+    65,536 distinct presentations issued and shown on the device are all accepted, 500 items with one flipped bit anywhere in their
+    143 words are rejected and nothing else is, a sample (honest and corrupted) gets the oracle's verdicts."""
+    import torch
+    from aeonflux_b200 import Issuer
+    from bench import KINDS_S16, load_issuer, synthesize_on_device
+    sp, ip, sk = load_issuer("issuer16.bin")
+    orc = coracle.Issuer(sp, ip, sk)
+    iss = Issuer(sp, ip, sk, device=0, max_batch=65536)
+    dev = synthesize_on_device(torch, iss, 65536, 78, torch.cuda.current_stream(), KINDS_S16, "keypair16.bin")
+    big = np.ascontiguousarray(dev.cpu().numpy().transpose(1, 0, 2))
+    del dev
+    assert big.shape == (65536, 143, 32)
+    assert not iss.verify_wire(KINDS_S16, big).any()
+    rng = np.random.default_rng(4)
+    bad = rng.choice(65536, 500, replace=False)
+    for j, i in enumerate(bad):
+        big[i, rng.integers(0, 143), 31 if j % 4 == 0 else rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+    v = iss.verify_wire(KINDS_S16, big)
+    expect = np.zeros(65536, np.uint8)
+    expect[bad] = 1
+    assert (v == expect).all()
+    sample = np.concatenate([bad[:48], rng.choice(65536, 16, replace=False)])
+    ov, _ = orc.verify_presentations(KINDS_S16, np.ascontiguousarray(big[sample]))
+    assert (v[sample] == ov).all()
+    iss.close()
+
+
 @pytest.mark.parametrize("name", GOLDEN_SHAPES)
 def test_issue_golden_shapes(coracle, name):
     """Issuer::issue (issuer.rs:111-124) on the GPU with supplied rng output: the committed Python-oracle fixture, then a
