@@ -349,6 +349,13 @@ int afx_bind_thread_to_device(int device);
 const char* afx_strerror(int code);
 const char* afx_version(void);
 
+/* Environment (read by the library, all optional):
+ *   AFX_CTAB16_BUDGET_MB   device-memory budget for the radix-2^16 constant tables of one issuer (default 200; 0 = radix 4096 only)
+ *   AFX_COPY_PARTS         1..8: contiguous item ranges a one-pass item-major host call copies its batch in, the early per-item
+ *                          stages of range k running under the copy of range k + 1 (default 4)
+ *   AFX_RLC_LEAF           smallest range the bisection of a failing random-linear-combination chunk descends to (default 1024)
+ *   AFX_STREAM_TRACE       non-empty: afx_stream_* logs every bucket submission and retirement with timestamps to stderr */
+
 #ifdef __cplusplus
 }
 #endif
