@@ -7,7 +7,9 @@ UndefinedBehaviorSanitizer and driven with adversarial wire input through every 
     encodings, random bytes, valid words in the wrong place, bit flips incl. the top byte), both constant-table radices;
   * random attribute shapes through verify / show / issue / BatchableProof exact + RLC (tests/test_random_shapes.py);
   * garbage into the prover calls (afx_issue*, afx_show*: undecodable attribute points, scalars >= l, random rng bytes) and wholly
-    random items into every verifier call, SoA and item-major, chunked and one-pass.
+    random items into every verifier call, SoA and item-major, chunked and one-pass;
+  * every third round the library-owned host layers: afx_stream_* (mixed shapes, corrupted records, several pushes, reuse after a
+    flush) and afx_multi_* (three contexts, three library threads).
 
 Any out-of-bounds access, use after free, misaligned or overflowing arithmetic aborts the run (the GPU-side counterpart is
 compute-sanitizer over tests/tools/sanitize_small.py, profiles/r02_compute_sanitizer.txt).
@@ -99,6 +101,11 @@ def main(seconds, light=False):
         except AfxError:
             pass
         iss.close()
+        # 4. the library-owned host layers: the mixed-shape stream object and the multi-device handle (their threads, buckets, slices)
+        if not light and rounds % 3 == 0:
+            from tests.test_sharding import run_mixed_stream, run_multi_gpu_issuer
+            run_mixed_stream(coracle, emu, 0, n4=11, n16=3, max4=int(rng.integers(2, 6)), max16=2, share_context=bool(rounds % 2))
+            run_multi_gpu_issuer(coracle, emu, devices=[0, 0, 0], count=int(rng.integers(7, 20)), max_batch=4)
         rounds += 1
         if time.time() - t0 > seconds:
             break
