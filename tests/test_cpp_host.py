@@ -62,3 +62,34 @@ def test_cpp_host_mirror_on_gpu(tmp_path, coracle):
     out = subprocess.run([exe, str(fx), "512"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host_parity ok: 1000 items, 143 rejected" in out.stdout and "cuda sm_100a" in out.stdout
+
+
+STRESS = os.path.join(ROOT, "tests", "cpp", "thread_stress.cpp")
+
+
+def test_threads_on_one_context_under_thread_sanitizer(tmp_path, coracle):
+    """tests/cpp/thread_stress.cpp: four threads making synchronous calls on one context, then a submit/wait streamer beside two
+    synchronous callers -- right verdicts or AFX_ERR_ARG, never a wrong verdict -- and the C++ host mirror incl. the library's
+    afx_multi_* device threads (host_parity.cpp), all against an emulation build compiled with ThreadSanitizer."""
+    rt = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    tsan = ["-fsanitize=thread", "-g"] if os.path.isabs(rt) and os.path.exists(rt) else []
+    emu_src = os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden"] + tsan + ["-x", "c++", "-o", str(tmp_path / "libafx_hostemu.so"), emu_src])
+    fx = tmp_path / "fixture.bin"
+    write_fixture(fx, coracle, 20)
+    for src, args, expect in ((STRESS, ["8", "3"], "thread_stress ok"), (SRC, ["8"], "host_parity ok: 20 items, 3 rejected")):
+        exe = str(tmp_path / os.path.basename(src).replace(".cpp", ""))
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread"] + tsan + ["-o", exe, src, "-L" + str(tmp_path), "-lafx_hostemu", "-Wl,-rpath," + str(tmp_path)])
+        out = subprocess.run([exe, str(fx)] + args, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and expect in out.stdout and "ThreadSanitizer" not in out.stderr, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_threads_on_one_context_on_gpu(tmp_path, coracle):
+    from aeonflux_b200.build import CSRC
+    fx = tmp_path / "fixture.bin"
+    write_fixture(fx, coracle, 2000)
+    exe = str(tmp_path / "thread_stress_cuda")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-o", exe, STRESS, "-L" + CSRC, "-laeonflux_b200", "-Wl,-rpath," + CSRC])
+    out = subprocess.run([exe, str(fx), "600", "20"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "thread_stress ok" in out.stdout and "cuda sm_100a" in out.stdout, out.stdout + out.stderr
