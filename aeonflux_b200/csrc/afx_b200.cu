@@ -104,6 +104,32 @@ __global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_ladders(Workspace ws,
     msm_job(ws, d, item, scratch + threadIdx.x, blockDim.x, ctab_of, active);
 }
 
+// Small batches: the aMAC ladder cut into parts (engine.cuh:amac_part_job) beside the constraint MSMs that do not need Z -- no job of
+// this grid depends on another, so there are no flags and no ticket; k_amac_combine and the "Z" constraint follow in stream order.
+struct PartsArgs {
+    const MsmDesc* msms; const u32* group_idx; u32 scratch_terms;
+    const AmacDesc* amac; u32* parts_out; u32 n_parts, nx;
+    AmacPart parts[MAX_AMAC_PARTS];
+};
+__global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_ladders_parts(Workspace ws, PartsArgs a) {
+    extern __shared__ __align__(16) u32 smem[];
+    const u32 job = blockIdx.x / a.nx, bx = blockIdx.x % a.nx;
+    u32 item = bx * blockDim.x + threadIdx.x;
+    bool active = item < ws.count;
+    if (!active) item = ws.count - 1;
+    if (job < a.n_parts) {
+        amac_part_job(ws, *a.amac, a.parts[job], a.parts_out + (size_t)job * ws.count * 32, item, smem + threadIdx.x, blockDim.x, active);
+        return;
+    }
+    const MsmDesc& d = a.msms[a.group_idx[job - a.n_parts]];
+    CtabResolver ctab_of{ws.ctabs, &d};
+    msm_job(ws, d, item, smem + threadIdx.x, blockDim.x, ctab_of, active);
+}
+__global__ void __launch_bounds__(128) k_amac_combine(Workspace ws, const AmacDesc* d, const u32* parts, u32 n_parts) {
+    u32 item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < ws.count) amac_combine_job(ws, *d, parts, n_parts, item);
+}
+
 // Issuer::issue: the same per-(item, job) ladders with every lookup constant-address (all scalars are secrets)
 __global__ void __launch_bounds__(TPB_MSM, AFX_MSM_MINB) k_msm_ct(Workspace ws, const MsmDesc* msms, const u32* group_idx) {
     extern __shared__ __align__(16) u32 smem[];
@@ -357,8 +383,20 @@ static void be_launch_points(const Workspace& ws, const PointJob* d_jobs, u32 nj
     k_points<<<grid_for(ws.e_hi - ws.e_lo, TPB, njobs), TPB, 0, s>>>(ws, d_jobs);
 }
 // The opt-in to > 48 KiB of dynamic shared memory is a per-device function attribute: set it once per (kernel, device).
+static int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 static void allow_large_smem(const void* kernel, int which) {
-    static std::atomic<bool> done[2][64];          // contexts on different devices are driven from different host threads
+    static std::atomic<bool> done[3][64];          // contexts on different devices are driven from different host threads
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !done[which][dev].load(std::memory_order_acquire)) {
@@ -370,8 +408,7 @@ static void allow_large_smem(const void* kernel, int which) {
 // One launch for the aMAC ladder (if `amac`) plus the MSMs of one scratch-size group.
 // The last n_dep_jobs entries of d_idx are the MSMs that wait on the aMAC flags.
 static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac_nps, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 n_dep_jobs,
-                             u32 max_terms, u32 max_con, int dep_msm, u32* flags, u32 epoch, u32 flag_tpb, u32* ticket, be_stream s) {
-    (void)max_con;
+                             u32 max_terms, u32 amac_terms, int dep_msm, u32* flags, u32 epoch, u32 flag_tpb, u32* ticket, be_stream s) {
     u32 terms = max_terms > amac_nps ? max_terms : amac_nps;
     // largest CTA (<= TPB_MSM threads) whose digit scratch fits in shared memory
     u32 tpb = TPB_MSM;
@@ -384,12 +421,46 @@ static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 amac
     const u32 nx = (ws.count + tpb - 1) / tpb;
     const u32 n_dep = n_dep_jobs < nidx ? n_dep_jobs : nidx, n_ind = nidx - n_dep;
     const u32 head = n_ind * nx + (amac ? nx : 0);
-    u32 stride = amac ? (u32)((uint64_t)head * 7 / 10 / nx) : 1;   // aMAC CTAs spread over the first 70% of the independent work
-    if (stride < 1) stride = 1;
+    // aMAC CTAs are spread over the first part of the independent work (one per `stride` positions) so that only a fraction of the SMs
+    // stream aMAC tables at any time: the first 70 % when the launch is many waves long (README-4, 65,536 items: 50 % 21.32 ms, 70 %
+    // 21.34, 90 % 22.46, 100 % 23.87).  But an aMAC CTA runs `a_rel` times as long as a constraint CTA (2 + n bases, scans) and the "Z"
+    // constraint waits for it, so the last one has to START a_rel + 1.5 CTA-durations before the grid would otherwise end -- in a
+    // short launch that means earlier than 70 %, down to "all aMAC CTAs first".  ms per synchronous call, fixed 70 % -> this rule:
+    // README-4 16,384 items 9.97 -> 8.16, 32,768: 14.11 -> 13.07, 65,536: 25.17 -> 25.15; S16 16,384: 33.3 -> 29.5, 32,768: 66.8 -> 59.2,
+    // 65,536: 117.2 -> 116.9 (the estimate's two constants were varied by +-40 %: no difference).
+    u32 stride = 1;
+    if (amac) {
+        const double a_rel = (99.0 + 37.0 * amac_terms) / 140.0;
+        const double waves = ((double)n_ind * nx + a_rel * nx + (double)n_dep * nx) / (2.0 * sm_count());
+        double frac = (waves - a_rel - 1.5) / waves;
+        if (frac > 0.7) frac = 0.7;
+        if (frac > 0) stride = (u32)((double)head * frac / nx);
+        if (stride < 1) stride = 1;
+    }
     LadderArgs a{d_msms, d_idx, terms, amac, flags, epoch, amac ? tpb : flag_tpb, dep_msm, ticket, nx, n_ind, n_dep, stride};
     cudaMemsetAsync(ticket, 0, 4, s);
     k_ladders<<<nx * (nidx + (amac ? 1 : 0)), tpb, smem, s>>>(ws, a);
     return tpb;
+}
+static void be_launch_ladders_parts(const Workspace& ws, const AmacDesc* amac, const AmacPart* parts, u32 n_parts, u32 part_terms, u32* parts_out,
+                                    const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 max_terms, be_stream s) {
+    u32 terms = max_terms > part_terms ? max_terms : part_terms;
+    if (terms < 1) terms = 1;
+    u32 tpb = TPB_MSM;
+    size_t smem = 0;
+    for (;; tpb /= 2) {
+        smem = (size_t)terms * 8 * tpb * 4;
+        if (smem <= LADDER_SMEM_BUDGET || tpb <= 32) break;
+    }
+    allow_large_smem((const void*)k_ladders_parts, 2);
+    PartsArgs a;
+    a.msms = d_msms; a.group_idx = d_idx; a.scratch_terms = terms; a.amac = amac; a.parts_out = parts_out; a.n_parts = n_parts;
+    a.nx = (ws.count + tpb - 1) / tpb;
+    for (u32 k = 0; k < (u32)MAX_AMAC_PARTS; k++) a.parts[k] = k < n_parts ? parts[k] : AmacPart{0, 0, 0, 0};
+    k_ladders_parts<<<a.nx * (n_parts + nidx), tpb, smem, s>>>(ws, a);
+}
+static void be_launch_amac_combine(const Workspace& ws, const AmacDesc* amac, const u32* parts_out, u32 n_parts, be_stream s) {
+    k_amac_combine<<<grid_for(ws.count, 128, 1), 128, 0, s>>>(ws, amac, parts_out, n_parts);
 }
 static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* d_msms, const u32* d_idx, u32 nidx, u32 max_terms, be_stream s) {
     u32 tpb = TPB_MSM;

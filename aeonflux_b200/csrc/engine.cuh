@@ -416,6 +416,56 @@ AFX_HD void amac_job(const Workspace& ws, const AmacDesc& d, u32 item, u32* scra
     }
 }
 
+// Small batches (api_impl.inc:run_pipeline): an item's aMAC ladder is the longest dependent chain of the pipeline -- 2 + n bases
+// walked by ONE thread, then the "Z" constraint -- and when the batch cannot fill the chip that chain IS the call's latency.  The
+// ladder is then cut into parts: part p takes the variable terms [var_lo, var_hi) and the revealed-scalar terms [ps_lo, ps_hi) of
+// the same AmacDesc through the same constant-schedule ladder (every table entry read and masked, no digit skipped) with its own
+// doublings and leaves its partial sum in extended coordinates; amac_combine_job subtracts the partial sums from C_V - W.  The
+// result is the same group element, hence the same bytes.
+struct AmacPart { u16 var_lo, var_hi, ps_lo, ps_hi; };
+constexpr int MAX_AMAC_PARTS = 24;
+AFX_HD void amac_part_job(const Workspace& ws, const AmacDesc& d, const AmacPart& p, u32* part_out /*[count][32]*/, u32 item, u32* scratch, u32 scratch_stride,
+                          bool active = true) {
+    for (u32 k = p.ps_lo; k < p.ps_hi; k++) {
+        sc m = sc_from_words(field_ptr(ws, d.ps[k].field_m, item));
+        sc y = sc_from_words(ws.secsc + 8 * d.ps[k].y_row);
+        u32 rec[8];
+        sc_recode16(rec, sc_mul(y, m));
+        for (int w = 0; w < 8; w++) scratch[((k - p.ps_lo) * 8 + w) * scratch_stride] = rec[w];
+    }
+    gc cacc = gc_identity();
+    for (int i = 63; i >= 0; i--) {
+#if defined(__CUDA_ARCH__)
+        AFX_STEP_SYNC();
+#endif
+        if (i != 63) gc_dbl4(cacc);
+        for (u32 k = p.var_lo; k < p.var_hi; k++) {
+            int dig = sc_digit16(ws.secdig + 8 * d.var[k].digit_row, i);
+            pniels e = pniels_scan_select_t(atab_ptr(ws, d.var[k].atab_slot, item), dig);
+            GE_LADDER_ADD(cacc, e);
+        }
+        for (u32 k = p.ps_lo; k < p.ps_hi; k++) {
+            u32 word = scratch[((k - p.ps_lo) * 8 + (i >> 3)) * scratch_stride];
+            int dig = ((int)(word << (28 - 4 * (i & 7)))) >> 28;
+            aniels e = aniels_scan_select8(ws.ctabs + (size_t)d.ps[k].ctab * CTAB_ENTRIES * 24, dig);
+            GE_LADDER_MADD(cacc, e);
+        }
+    }
+    for (u32 k = 0; k < (u32)(p.ps_hi - p.ps_lo) * 8u; k++) scratch[k * scratch_stride] = 0;   // wipe the recoded y_i * m_i
+    ge acc = gc_to_ge(cacc);
+    if (active) store_ge(part_out + (size_t)item * 32, acc);
+}
+AFX_HD void amac_combine_job(const Workspace& ws, const AmacDesc& d, const u32* parts /*[n_parts][count][32]*/, u32 n_parts, u32 item) {
+    ge cv = load_ge(ext_ptr(ws, d.ext_cv, item));
+    ge z = ge_add_pn(cv, pniels_cneg(load_pniels(ws.W_pniels), 1));      // Z = (C_V - W) - sum of the parts
+    for (u32 g = 0; g < n_parts; g++) z = ge_sub(z, load_ge(parts + ((size_t)g * ws.count + item) * 32));
+    u32 w[8];
+    ge_compress(w, z);
+    store8(comp_ptr(ws, d.out_comp_slot, item), w);
+    if (!ws.no_tables) store_table8(table_ptr(ws, d.out_table_slot, item), z);
+    if (d.out_ext_slot != 0xffff) store_ge(ext_ptr(ws, d.out_ext_slot, item), z);
+}
+
 AFX_HD void ztable_job(const Workspace& ws, const AmacDesc& d, u32 item) {
     store_table8(table_ptr(ws, d.out_table_slot, item), load_ge(ext_ptr(ws, d.out_ext_slot, item)));
 }

@@ -55,6 +55,20 @@ static u32 be_launch_ladders(const Workspace& ws, const AmacDesc* amac, u32 nps,
     }
     return 1;
 }
+static void be_launch_ladders_parts(const Workspace& ws, const AmacDesc* amac, const AmacPart* parts, u32 n_parts, u32 part_terms, u32* parts_out,
+                                    const MsmDesc* msms, const u32* idx, u32 nidx, u32 max_terms, be_stream) {
+    std::vector<u32> scratch((size_t)(max_terms > part_terms ? max_terms : part_terms) * 8 + 8);
+    for (u32 g = 0; g < n_parts; g++)
+        for (u32 i = 0; i < ws.count; i++) amac_part_job(ws, *amac, parts[g], parts_out + (size_t)g * ws.count * 32, i, scratch.data(), 1);
+    for (u32 k = 0; k < nidx; k++) {
+        const MsmDesc& d = msms[idx[k]];
+        CtabResolver r{ws.ctabs, &d};
+        for (u32 i = 0; i < ws.count; i++) msm_job(ws, d, i, scratch.data(), 1, r);
+    }
+}
+static void be_launch_amac_combine(const Workspace& ws, const AmacDesc* amac, const u32* parts_out, u32 n_parts, be_stream) {
+    for (u32 i = 0; i < ws.count; i++) amac_combine_job(ws, *amac, parts_out, n_parts, i);
+}
 static void be_launch_msm_ct(const Workspace& ws, const MsmDesc* msms, const u32* idx, u32 nidx, u32 max_terms, be_stream) {
     std::vector<u32> scratch((size_t)max_terms * 8);
     for (u32 k = 0; k < nidx; k++) for (u32 i = 0; i < ws.count; i++) msm_ct_job(ws, msms[idx[k]], i, scratch.data(), 1);

@@ -534,3 +534,11 @@ def test_linked_full_size_round_trip(readme4):
         wire[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
     expect = np.zeros(count, np.uint8); expect[bad] = 1
     assert (iss.verify_wire(kinds, wire, linked=True) == expect).all()
+
+
+def test_split_amac_ladder_on_gpu(coracle, monkeypatch):
+    """Small batches run the aMAC ladder in parts (k_ladders_parts, k_amac_combine): same Z, commitments, challenges, verdicts for every
+    cut; and a batch above the threshold still takes the single fused ladder."""
+    from aeonflux_b200 import Issuer
+    from tests.test_host_logic import check_split_amac
+    check_split_amac(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=4096), coracle, monkeypatch, count=700)

@@ -798,3 +798,37 @@ def test_single_pass_wire_call_copies_in_halves(emu, coracle):
     for m in (9, 8, 3, 2, 1):
         assert (iss.verify_wire(kinds, pres[:m]) == ov[:m]).all(), m
     assert (iss.verify_wire(bytes([0, 0, 2, 2]), issu, issuance=True) == oi).all() and list(ov) == [1, 0, 0, 0, 1, 0, 0, 0, 1]
+
+
+def check_split_amac(make_issuer, coracle, monkeypatch, count=7):
+    """Small batches cut the aMAC ladder into parts that run as separate jobs (api_impl.inc:amac_split_terms); whatever the cut -- none,
+    one term per part, two, five, the automatic choice -- Z, every commitment, every challenge and every verdict are the oracle's."""
+    from aeonflux_b200 import PresentationBatch
+    for n, rk, hide in ((4, b"SSPE", [0, 3]), (16, b"SSSSSSPP" + b"E" * 8, [0, 1] + list(range(8, 16))), (1, b"S", [])):
+        sp, ip, sk = coracle.make_issuer(n)
+        orc = coracle.Issuer(sp, ip, sk)
+        kinds, pres, _ = orc.synth(rk, hide, b"split-amac", 0, count, want_issuances=False)
+        pres[2, 1, 3] ^= 8
+        pres[4, 5 + sum(k == 1 for k in kinds), 0] ^= 2          # C_x_1: a base of the aMAC ladder
+        ov, _, tr = orc.verify_presentations(kinds, pres, trace=True)
+        assert ov[2] == 1 and ov[4] == 1
+        launches = {}
+        for mode in ("0", "1", "2", "5", None):
+            if mode is None:
+                monkeypatch.delenv("AFX_AMAC_SPLIT", raising=False)
+            else:
+                monkeypatch.setenv("AFX_AMAC_SPLIT", mode)
+            iss = make_issuer(sp, ip, sk)
+            v, dbg = iss.verify_batch(PresentationBatch.from_items(kinds, pres), debug=True)
+            compare_with_oracle_trace(v, dbg, ov, tr)
+            assert (iss.verify_wire(kinds, pres) == ov).all()
+            launches[mode] = iss.launch_count
+            iss.close()
+        if n > 1:
+            assert launches["1"] > launches["0"] and launches[None] > launches["0"]      # the split path ran (combine + "Z" launches)
+    monkeypatch.delenv("AFX_AMAC_SPLIT", raising=False)
+
+
+def test_split_amac_ladder_on_emulation(emu, coracle, monkeypatch):
+    from aeonflux_b200 import Issuer
+    check_split_amac(lambda sp, ip, sk: Issuer(sp, ip, sk, max_batch=16, _binding=emu), coracle, monkeypatch)
