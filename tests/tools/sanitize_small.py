@@ -20,6 +20,11 @@ for n, rk, hide, count in ((4, b"SSPE", [0, 3], 300), (3, b"SES", [1], 70), (16,
     ov, _ = orc.verify_presentations(kinds, pres)
     assert (v == ov).all()
     assert (iss.verify_wire(kinds, pres) == ov).all()
+    os.environ["AFX_AMAC_SPLIT"] = "0"      # small batches cut the aMAC ladder into parts (k_ladders_parts); this is the single fused ladder with its ticket and flags
+    assert (iss.verify_wire(kinds, pres) == ov).all()
+    os.environ["AFX_AMAC_SPLIT"] = "1"
+    assert (iss.verify_wire(kinds, pres) == ov).all()
+    del os.environ["AFX_AMAC_SPLIT"]
     res, st = iss.show_batch(kinds, np.ascontiguousarray(showin.transpose(1, 0, 2)))
     assert (res.fields.transpose(1, 0, 2) == pres).all()
     ik = bytes(0 if c == ord("S") else 2 for c in rk)
