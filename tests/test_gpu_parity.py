@@ -542,3 +542,30 @@ def test_split_amac_ladder_on_gpu(coracle, monkeypatch):
     from aeonflux_b200 import Issuer
     from tests.test_host_logic import check_split_amac
     check_split_amac(lambda sp, ip, sk: Issuer(sp, ip, sk, device=0, max_batch=4096), coracle, monkeypatch, count=700)
+
+
+@pytest.mark.parametrize("count", [9000, 20000, 40000])
+def test_medium_batches_place_their_amac_ctas_early(readme4, count):
+    """Between the split small-batch path (<= 8,192 items) and the many-wave launch, the fused ladder grid places its aMAC CTAs by how
+    long the launch is (afx_b200.cu:be_launch_ladders); the block order changes, the bytes must not: distinct items made on the
+    device, flipped bits rejected, nothing else, a sample against the oracle."""
+    import torch
+    from aeonflux_b200 import Issuer
+    from bench import KINDS_README4, synthesize_on_device
+    orc, _, (sp, ip, sk) = readme4
+    iss = Issuer(sp, ip, sk, device=0, max_batch=count)
+    dev = synthesize_on_device(torch, iss, count, 500 + count, torch.cuda.current_stream())
+    big = np.ascontiguousarray(dev.cpu().numpy().transpose(1, 0, 2))
+    assert not iss.verify_wire(KINDS_README4, big).any()
+    rng = np.random.default_rng(count)
+    bad = rng.choice(count, 200, replace=False)
+    for i in bad:
+        big[i, rng.integers(0, 28), rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+    v = iss.verify_wire(KINDS_README4, big)
+    expect = np.zeros(count, np.uint8)
+    expect[bad] = 1
+    assert (v == expect).all()
+    sample = np.concatenate([bad[:40], rng.choice(count, 24, replace=False)])
+    ov, _ = orc.verify_presentations(KINDS_README4, np.ascontiguousarray(big[sample]))
+    assert (v[sample] == ov).all()
+    iss.close()
