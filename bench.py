@@ -498,6 +498,23 @@ def secondary_measurements(torch, issuer4, items4, local, stream, flush, B, step
                          "frac": (B * 2 * wm["total"] / (ms * 1e-3)) / imad_peak, "kernels": kern,
                          "cpu_baseline": {"value": rate16, "unit": "presentations/s", "cores": cores, "kind": "port",
                                           "sample": "%d items of the same batch, %.1f s, oracle/c reference schedule; verdicts identical" % (sample16, wall16)}}
+    # ---- small batches: latency of ONE synchronous item-major call (copy in, kernels, verdicts out) -- what a serving front end sees
+    def call_ms(iss, kinds, w, count):
+        iss.verify_wire(kinds, w[:count])
+        ts = []
+        for _ in range(9):
+            t0 = time.perf_counter()
+            v = iss.verify_wire(kinds, w[:count])
+            ts.append(time.perf_counter() - t0)
+        assert not v[:min(count, 5)].any()
+        return 1e3 * float(np.median(ts))
+    w4 = torch.empty((8192, WORDS, 32), dtype=torch.uint8).pin_memory()
+    w4.numpy()[:] = items4[:8192]
+    out["small_batch_latency"] = {"workload": "one synchronous afx_verify_presentations_wire call of 1 / 1,024 / 8,192 presentations from page-locked memory, median wall clock of 9 calls",
+                                  "unit": "ms per call",
+                                  "readme4": {str(c): call_ms(issuer4, KINDS_README4, w4.numpy(), c) for c in (1, 1024, 8192)},
+                                  "s16": {str(c): call_ms(issuer16, KINDS_S16, w16[8:], c) for c in (1, 1024, 8192)},
+                                  "note": "passes of at most 8,192 items run the aMAC ladder in parts beside the constraint MSMs (DESIGN.md section 5, Small batches)"}
     issuer16.close()
     return out
 
