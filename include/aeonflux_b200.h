@@ -356,6 +356,7 @@ const char* afx_version(void);
  *   AFX_AMAC_SPLIT         0: never cut the aMAC ladder of a small pass into parts; g > 0: g terms per part for every pass of at most
  *                          32,768 items (default: passes of at most 8,192 items, 2 or 4 terms per part -- DESIGN.md section 5)
  *   AFX_RLC_LEAF           smallest range the bisection of a failing random-linear-combination chunk descends to (default 1024)
+ *   AFX_STREAM_RAMP_DIV    afx_stream_*: the first bucket after a flush is 1/div of a full one, later ones double (default 8; 1 = no ramp)
  *   AFX_STREAM_TRACE       non-empty: afx_stream_* logs every bucket submission and retirement with timestamps to stderr */
 
 #ifdef __cplusplus
