@@ -56,4 +56,26 @@ for name, kinds, issuer_file, kp in (("README-4", KINDS_README4, "issuer4.bin", 
     iss.close()
     del wire
     torch.cuda.empty_cache()
+# configs[2] in small: Issuer::issue (item-major requests in, issuances out) and CredentialIssuance::verify of the result
+if "--no-issuance" not in sys.argv:
+    sp, ip, sk = load_issuer("issuer4.bin")
+    iss = Issuer(sp, ip, sk, device=0, max_batch=8192)
+    kinds, n = bytes([0, 0, 2, 2]), 4
+    rng = np.random.default_rng(7)
+    pts, _ = iss.selftest_primitive("from_uniform", rng.integers(0, 256, (2 * 8192, 64), dtype=np.uint8))
+    req = np.empty((8192, 3 * n + 14, 32), np.uint8)
+    sc = rng.integers(0, 256, (8192, 2, 32), dtype=np.uint8); sc[:, :, 31] &= 0x0f
+    req[:, 0:2] = sc; req[:, 2:4] = pts.reshape(8192, 2, 32)
+    req[:, 4:] = rng.integers(0, 256, (8192, 3 * n + 10, 32), dtype=np.uint8)
+    for count in (1, 1024, 8192):
+        r = np.ascontiguousarray(req[:count])
+        issued, st = iss.issue_wire(kinds, r)
+        assert not st.any() and not iss.verify_wire(kinds, issued, issuance=True).any()
+        ti, tv = [], []
+        for _ in range(9):
+            t0 = time.perf_counter(); iss.issue_wire(kinds, r); ti.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); iss.verify_wire(kinds, issued, issuance=True); tv.append(time.perf_counter() - t0)
+        out["rows"].append({"shape": "issuance n=4", "items": count, "ms_issue_wire": round(1e3 * float(np.median(ti)), 3),
+                            "ms_verify_issuances_wire": round(1e3 * float(np.median(tv)), 3)})
+    iss.close()
 print(json.dumps(out, indent=1))
