@@ -245,3 +245,70 @@ impl Drop for B200Multi {
         unsafe { afx_multi_destroy(self.m) }
     }
 }
+
+/// Records of several shapes arriving interleaved (`afx_stream_*`; BASELINE configs[4]): each record is bucketed by shape into
+/// page-locked buffers and every full bucket is verified asynchronously.  The library writes a record's verdict to the address it
+/// was given at `push` whenever that record's bucket completes, so the verdict bytes must not move or be read before `flush`: the
+/// stream owns them (a `Vec` allocated once for `max_records`, never grown) and hands them out only from `flush`.
+/// The contexts registered with `add_shape` must outlive the stream (`'a`).
+pub struct B200Stream<'a> {
+    s: *mut afx_stream,
+    record_bytes: Vec<usize>,
+    verdicts: Vec<u8>,          // len = records pushed since the last flush; capacity fixed at construction
+    _contexts: std::marker::PhantomData<&'a B200Context>,
+}
+
+impl<'a> B200Stream<'a> {
+    /// `max_records`: the most records that will be pushed between two flushes.
+    pub fn new(max_records: usize) -> Result<B200Stream<'a>, B200Error> {
+        let mut s: *mut afx_stream = std::ptr::null_mut();
+        let rc = unsafe { afx_stream_create(&mut s) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(B200Stream { s, record_bytes: Vec::new(), verdicts: Vec::with_capacity(max_records), _contexts: std::marker::PhantomData })
+    }
+
+    /// Registers a shape (presentations of `kinds`, or issuances when `issuance`) verified on `ctx`; returns its shape id.
+    pub fn add_shape(&mut self, ctx: &'a B200Context, issuance: bool, kinds: &[u8]) -> Result<u8, B200Error> {
+        let (mut id, mut bytes): (c_int, usize) = (0, 0);
+        let rc = unsafe { afx_stream_add_shape(self.s, ctx.ctx, issuance as c_int, kinds.len() as u16, kinds.as_ptr(), &mut id, &mut bytes) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        self.record_bytes.push(bytes);
+        Ok(id as u8)
+    }
+
+    /// `records`: concatenated records (copied into the stream's buckets before this returns); `offsets[i]` / `shape_ids[i]`: where
+    /// record i starts and which registered shape it has.  Returns the position of the first of these records in the verdict
+    /// vector `flush` will return.
+    pub fn push(&mut self, records: &[u8], offsets: &[u64], shape_ids: &[u8]) -> Result<usize, B200Error> {
+        let n = offsets.len();
+        if shape_ids.len() != n || self.verdicts.len() + n > self.verdicts.capacity() { return Err(B200Error(-1)); }
+        for (o, id) in offsets.iter().zip(shape_ids.iter()) {
+            match self.record_bytes.get(*id as usize) {
+                Some(len) if (*o as usize).checked_add(*len).map_or(false, |end| end <= records.len()) => {},
+                _ => return Err(B200Error(-1)),
+            }
+        }
+        let first = self.verdicts.len();
+        self.verdicts.resize(first + n, 0);          // within the capacity: the buffer does not move
+        let rc = unsafe {
+            afx_stream_push(self.s, records.as_ptr(), offsets.as_ptr(), shape_ids.as_ptr(), n, self.verdicts.as_mut_ptr().add(first))
+        };
+        if rc != 0 { return Err(B200Error(rc)); }
+        Ok(first)
+    }
+
+    /// Submits the partly filled buckets, waits for everything in flight and returns the verdicts of every record pushed since the
+    /// last flush, in push order (0 = Ok, 1 = VerificationFailure).
+    pub fn flush(&mut self) -> Result<Vec<u8>, B200Error> {
+        let rc = unsafe { afx_stream_flush(self.s) };
+        if rc != 0 { return Err(B200Error(rc)); }
+        let cap = self.verdicts.capacity();
+        Ok(std::mem::replace(&mut self.verdicts, Vec::with_capacity(cap)))
+    }
+}
+
+impl<'a> Drop for B200Stream<'a> {
+    fn drop(&mut self) {
+        unsafe { afx_stream_destroy(self.s) }      // waits for outstanding buckets (they write into self.verdicts) before anything is freed
+    }
+}
